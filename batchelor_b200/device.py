@@ -1,0 +1,223 @@
+"""Device-resident wrappers over the ``b200mnn_dev_*`` C ABI.
+
+torch supplies device memory, the current CUDA stream and (optionally) the ``torch.distributed`` process group;
+every numeric step is a kernel of libb200mnn.  Tensors are fp64, row-major ``[cells x dims]``; ids are int32,
+0-based.  Nothing here falls back to torch math when the library or the GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_launches = 0  # kernels of libb200mnn launched through this module (bench.py reports it as gpu_launches)
+
+
+def launches() -> int:
+    return _launches
+
+
+def _count(n: int) -> None:
+    global _launches
+    _launches += n
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f64(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float64 or not t.is_cuda:
+        raise TypeError("expected a CUDA float64 tensor")
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise TypeError("expected a CUDA tensor")
+    return t.to(torch.int32).contiguous()
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise _lib.B200Error(2, "no usable CUDA device: batchelor_b200 has no CPU fallback")
+    _lib.load()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# a1: exact kNN
+# ----------------------------------------------------------------------------------------------------------
+def query_knn(X: torch.Tensor, Q: torch.Tensor, k: int, want_dist: bool = True, stats: Optional[torch.Tensor] = None
+              ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """k nearest rows of X for every row of Q: (idx int32 [nq,k] 0-based, dist float64 [nq,k] or None)."""
+    X = _f64(X); Q = _f64(Q)
+    n, d = X.shape
+    nq = Q.shape[0]
+    if Q.shape[1] != d:
+        raise ValueError("X and query must have the same number of dimensions")
+    idx = torch.empty((nq, k), dtype=torch.int32, device=X.device)
+    dist = torch.empty((nq, k), dtype=torch.float64, device=X.device) if want_dist else None
+    _lib.call("b200mnn_dev_query_knn", _p(X), n, _p(Q), nq, d, k, _p(idx), _p(dist), _p(stats), _stream())
+    _count(8)
+    return idx, dist
+
+
+def query_knn_sharded(X: torch.Tensor, Q: torch.Tensor, k: int, want_dist: bool = True, min_rows_per_rank: int = 2048
+                      ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Query-sharded kNN: the reference set X is replicated, rank r searches a contiguous block of query rows and the
+    per-shard (index, distance) blocks are all-gathered over NCCL.  Falls through to :func:`query_knn` when there is
+    no process group (or the problem is tiny)."""
+    import torch.distributed as dist_
+
+    if not (dist_.is_available() and dist_.is_initialized()) or dist_.get_world_size() == 1:
+        return query_knn(X, Q, k, want_dist)
+    ws, rank = dist_.get_world_size(), dist_.get_rank()
+    nq = Q.shape[0]
+    if nq < ws * min_rows_per_rank:
+        return query_knn(X, Q, k, want_dist)
+    per = (nq + ws - 1) // ws
+    lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
+    idx_l, dist_l = query_knn(X, Q[lo:hi], k, want_dist)
+    idx_pad = torch.zeros((per, k), dtype=torch.int32, device=X.device)
+    idx_pad[: hi - lo] = idx_l
+    idx_all = torch.empty((ws * per, k), dtype=torch.int32, device=X.device)
+    dist_.all_gather_into_tensor(idx_all, idx_pad)
+    dist_all = None
+    if want_dist:
+        d_pad = torch.zeros((per, k), dtype=torch.float64, device=X.device)
+        d_pad[: hi - lo] = dist_l
+        dist_all = torch.empty((ws * per, k), dtype=torch.float64, device=X.device)
+        dist_.all_gather_into_tensor(dist_all, d_pad)
+        dist_all = dist_all[:nq]
+    return idx_all[:nq], dist_all
+
+
+def debug_candidates(X: torch.Tensor, Q: torch.Tensor, k: int):
+    """Tensor-core scoring stage only: (cand_idx [nq,C], approx_d2 [nq,C], thr [nq])."""
+    X = _f64(X); Q = _f64(Q)
+    n, d = X.shape
+    nq = Q.shape[0]
+    cap = 8 * 64
+    cidx = torch.empty((nq, cap), dtype=torch.int32, device=X.device)
+    cd2 = torch.empty((nq, cap), dtype=torch.float64, device=X.device)
+    thr = torch.empty((nq,), dtype=torch.float64, device=X.device)
+    nc = C.c_int64(0)
+    _lib.call("b200mnn_dev_debug_candidates", _p(X), n, _p(Q), nq, d, k, _p(cidx), _p(cd2), _p(thr), cap, C.byref(nc), _stream())
+    c = nc.value
+    return cidx.view(-1)[: nq * c].view(nq, c), cd2.view(-1)[: nq * c].view(nq, c), thr
+
+
+# ----------------------------------------------------------------------------------------------------------
+# a3: mutual pairs
+# ----------------------------------------------------------------------------------------------------------
+def find_mutual_nns(left: torch.Tensor, right: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """left [n1,k2] ids into batch 2, right [n2,k1] ids into batch 1 (0-based) -> (first, second) int32, 0-based."""
+    left = _i32(left); right = _i32(right)
+    n1, k2 = left.shape
+    n2, k1 = right.shape
+    cap = max(1, n1 * k2)
+    first = torch.empty((cap,), dtype=torch.int32, device=left.device)
+    second = torch.empty((cap,), dtype=torch.int32, device=left.device)
+    npairs = torch.zeros((1,), dtype=torch.int64, device=left.device)
+    _lib.call("b200mnn_dev_find_mutual_nns", _p(left), n1, k2, _p(right), n2, k1, _p(first), _p(second), cap, _p(npairs), _stream())
+    _count(5)
+    m = int(npairs.item())
+    return first[:m], second[:m]
+
+
+def find_mutual_nn(data1: torch.Tensor, data2: torch.Tensor, k1: int, k2: int, sharded: bool = True):
+    """findMutualNN(data1, data2, k1, k2): two exact searches + mutual pairs.  Returns (first, second, w21, w12)."""
+    knn = query_knn_sharded if sharded else query_knn
+    k1 = min(k1, data1.shape[0]); k2 = min(k2, data2.shape[0])
+    w21, _ = knn(data2, data1, k2, want_dist=False)  # neighbours of batch-1 cells in batch 2
+    w12, _ = knn(data1, data2, k1, want_dist=False)  # neighbours of batch-2 cells in batch 1
+    first, second = find_mutual_nns(w21, w12)
+    return first, second, w21, w12
+
+
+# ----------------------------------------------------------------------------------------------------------
+# a4 / a8 / a6 / a9
+# ----------------------------------------------------------------------------------------------------------
+def average_correction(ref: torch.Tensor, cur: torch.Tensor, first: torch.Tensor, second: torch.Tensor):
+    ref = _f64(ref); cur = _f64(cur); first = _i32(first); second = _i32(second)
+    n1, d = ref.shape
+    n2 = cur.shape[0]
+    npairs = first.shape[0]
+    cap = max(1, min(npairs, n2))
+    averaged = torch.empty((cap, d), dtype=torch.float64, device=ref.device)
+    uniq = torch.empty((cap,), dtype=torch.int32, device=ref.device)
+    nmnn = torch.zeros((1,), dtype=torch.int64, device=ref.device)
+    _lib.call("b200mnn_dev_average_correction", _p(ref), n1, _p(cur), n2, d, _p(first), _p(second), npairs, _p(averaged), _p(uniq),
+              _p(nmnn), _stream())
+    _count(10)
+    m = int(nmnn.item())
+    return averaged[:m], uniq[:m]
+
+
+def center_along_batch_vector(mat: torch.Tensor, batch_vec: torch.Tensor, restrict: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """In place on a contiguous fp64 CUDA matrix; returns it."""
+    if not mat.is_contiguous():
+        raise ValueError("mat must be contiguous (the kernel works in place)")
+    mat = _f64(mat); batch_vec = _f64(batch_vec)
+    r = _i32(restrict) if restrict is not None else None
+    _lib.call("b200mnn_dev_center_along_batch_vector", _p(mat), mat.shape[0], mat.shape[1], _p(batch_vec), _p(r),
+              0 if r is None else r.shape[0], _stream())
+    _count(5)
+    return mat
+
+
+def tricube_apply(cur: torch.Tensor, correction: torch.Tensor, idx: torch.Tensor, dist: torch.Tensor, ndist: float) -> torch.Tensor:
+    cur = _f64(cur); correction = _f64(correction); idx = _i32(idx); dist = _f64(dist)
+    out = torch.empty_like(cur)
+    _lib.call("b200mnn_dev_tricube_apply", _p(cur), cur.shape[0], cur.shape[1], _p(correction), correction.shape[0], _p(idx), _p(dist),
+              idx.shape[1], float(ndist), _p(out), _stream())
+    _count(1)
+    return out
+
+
+def cosine_norm(x: torch.Tensor, want_matrix: bool = True):
+    """x [cells, genes] -> (normalised or None, l2norm [cells])."""
+    x = _f64(x)
+    out = torch.empty_like(x) if want_matrix else None
+    l2 = torch.empty((x.shape[0],), dtype=torch.float64, device=x.device)
+    _lib.call("b200mnn_dev_cosine_norm", _p(x), x.shape[0], x.shape[1], _p(out), _p(l2), _stream())
+    _count(1)
+    return out, l2
+
+
+# ----------------------------------------------------------------------------------------------------------
+# a5 / a7
+# ----------------------------------------------------------------------------------------------------------
+def smooth_gaussian_kernel(averaged: torch.Tensor, index0: torch.Tensor, mat: torch.Tensor, sigma2: float) -> torch.Tensor:
+    """averaged [nmnn, G], index0 int [nmnn] rows of mat, mat [ncells, Gdist] -> [ncells, G]."""
+    averaged = _f64(averaged); mat = _f64(mat); index0 = _i32(index0)
+    nmnn, G = averaged.shape
+    if index0.shape[0] != nmnn:
+        raise _lib.B200Error(1, "'index' must have length equal to number of rows in 'averaged'")
+    out = torch.empty((mat.shape[0], G), dtype=torch.float64, device=mat.device)
+    _lib.call("b200mnn_dev_smooth_gaussian_kernel", _p(averaged), G, nmnn, _p(index0), _p(mat), mat.shape[1], mat.shape[0], float(sigma2),
+              _p(out), _stream())
+    _count(6)
+    return out
+
+
+def adjust_shift_variance(data1: torch.Tensor, data2: torch.Tensor, vect: torch.Tensor, sigma2: float, r1: torch.Tensor,
+                          r2: torch.Tensor) -> torch.Tensor:
+    """data1 [n1,G], data2 [n2,G], vect [n2,G]; r1/r2 0-based int -> scaling [n2]."""
+    data1 = _f64(data1); data2 = _f64(data2); vect = _f64(vect); r1 = _i32(r1); r2 = _i32(r2)
+    if data1.shape[1] != data2.shape[1] or data1.shape[1] != vect.shape[1]:
+        raise _lib.B200Error(1, "number of genes do not match up between matrices")
+    if vect.shape[0] != data2.shape[0]:
+        raise _lib.B200Error(1, "number of cells do not match up between matrices")
+    out = torch.empty((data2.shape[0],), dtype=torch.float64, device=data2.device)
+    _lib.call("b200mnn_dev_adjust_shift_variance", _p(data1), data1.shape[0], _p(data2), data2.shape[0], data1.shape[1], _p(vect),
+              float(sigma2), _p(r1), r1.shape[0], _p(r2), r2.shape[0], _p(out), _stream())
+    _count(3)
+    return out

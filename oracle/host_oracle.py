@@ -50,7 +50,7 @@ def center_along_batch_vector(mat, batch_vec, restrict=None):
     mat = np.asarray(mat, dtype=np.float64)
     v = np.asarray(batch_vec, dtype=np.float64)
     v = v / math.sqrt(float(np.sum(v ** 2)))
-    loc = mat @ v
+    loc = (mat * v[None, :]).sum(axis=1)  # row-wise sums: identical rows give identical projections (BLAS gemv need not)
     central = loc.mean() if restrict is None else loc[np.asarray(restrict, dtype=np.int64) - 1].mean()
     return mat + np.outer(central - loc, v)
 

@@ -186,7 +186,7 @@ int oracle_smooth_gaussian_kernel(const double* averaged, int64_t G, int64_t nmn
         for (int64_t c = 0; c < ncells; ++c) {
             const double* mc = mat + c * Gdist;
             double* oc = out + c * G;
-            for (int64_t g = 0; g < G; ++g) oc[g] = 0.0;
+            for (int64_t g = 0; g < G; ++g) oc[g] = (nmnn == 0) ? NAN : 0.0; /* no MNN cell: 0 * exp(-Inf - NA) = NaN (:105-115) */
             if (nmnn == 0) continue;
             double total = 0.0, top = -INFINITY;
             for (int64_t i = 0; i < nmnn; ++i) {

@@ -1,0 +1,340 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI (host-buffer entry points via
+batchelor_b200.api, device-pointer entry points via batchelor_b200.device) and is compared with the CPU oracle on the
+same seeded inputs, and with the committed golden vectors produced by the reference's own object code.
+
+Bars: neighbour indices, distances' order and MNN pair lists are BIT-EXACT (0 mismatching slots, ties by index);
+floating-point outputs agree within 1e-5 relative (north_star), most far tighter.
+"""
+import numpy as np
+import pytest
+
+import batchelor_b200 as bb
+from batchelor_b200 import synth
+from oracle import capi, host_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north_star tolerance for floating-point outputs
+
+
+def _relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a1: exact kNN -- bit-exact indices and distances
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,nq,d,k", [
+    (1000, 700, 50, 20),      # the configured shape, small
+    (5000, 3000, 50, 20),
+    (300, 1000, 50, 20),      # fewer references than one tile
+    (4097, 129, 50, 1),       # k = 1, ragged tiles
+    (2000, 500, 50, 30),      # k > 24 -> 64-entry candidate lists
+    (2000, 500, 50, 56),
+    (2000, 300, 50, 60),      # k beyond the tensor path -> generic exact path
+    (1500, 400, 1, 5), (1500, 400, 2, 5), (1500, 400, 5, 7), (1500, 400, 6, 7), (1500, 400, 16, 7), (1500, 400, 17, 7),
+    (1500, 400, 32, 10), (1500, 400, 64, 10), (1500, 400, 100, 10), (800, 200, 192, 10),
+    (800, 200, 250, 10),      # d beyond the resident-operand kernel -> generic exact path
+    (40, 100, 50, 40),        # k = n
+])
+def test_query_knn_matches_oracle_bit_exact(n, nq, d, k):
+    X, Q = synth.pc_batches(2, [n, nq], d=d, ncomp=8)
+    got = bb.queryKNN(X, Q, k)
+    idx, dist = capi.query_knn(X, Q, k)
+    assert np.array_equal(got["index"], idx), f"{int((got['index'] != idx).sum())} mismatching neighbour slots"
+    assert np.array_equal(got["distance"], dist)  # same arithmetic, same summation order -> identical doubles
+
+
+def test_query_knn_column_major_inputs_like_r():
+    X, Q = synth.pc_batches(2, [1200, 900], d=50, ncomp=8)
+    got = bb.queryKNN(np.asfortranarray(X), np.asfortranarray(Q), 20)
+    idx, dist = capi.query_knn(X, Q, 20)
+    assert got["index"].flags.f_contiguous and np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_not_fp32_representable_inputs():
+    rng = np.random.default_rng(3)
+    X = rng.normal(size=(3000, 50)) * 7.3 + 100.0   # arbitrary doubles, far from the origin (hard for the split operands)
+    Q = rng.normal(size=(1000, 50)) * 7.3 + 100.0
+    got = bb.queryKNN(X, Q, 20)
+    idx, dist = capi.query_knn(X, Q, 20)
+    assert np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_tiny_and_huge_scales():
+    X, Q = synth.pc_batches(2, [2000, 600], d=50, ncomp=8)
+    for s in (1e-6, 3e4):
+        got = bb.queryKNN(X * s, Q * s, 20)
+        idx, dist = capi.query_knn(X * s, Q * s, 20)
+        assert np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_exact_ties_broken_by_index():
+    g = np.stack(np.meshgrid(np.arange(12.0), np.arange(12.0), indexing="ij"), -1).reshape(-1, 2)
+    X = np.vstack([g, g, g])        # every point three times: ties everywhere, incl. > 32 equidistant points
+    got = bb.queryKNN(X, g, 9)
+    idx, dist = capi.query_knn(X, g, 9)
+    assert np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+    X = np.zeros((500, 50)); X[:, 0] = np.repeat(np.arange(10.0), 50)   # 50 exact duplicates per location
+    Q = X[::7] + 0.0
+    got = bb.queryKNN(X, Q, 20)
+    idx, dist = capi.query_knn(X, Q, 20)
+    assert np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_k_capped_with_warning():
+    X, Q = synth.pc_batches(2, [10, 30], d=50, ncomp=2)
+    with pytest.warns(UserWarning, match="capped"):
+        got = bb.queryKNN(X, Q, 20)
+    idx, _ = capi.query_knn(X, Q, 10)
+    assert got["index"].shape == (30, 10) and np.array_equal(got["index"], idx)
+
+
+def test_query_knn_medium_against_kmknn_port():
+    """100k x 100k: brute-force oracle is too slow; the KMKNN port (itself pinned to brute force in test_oracle.py) checks."""
+    X, Q = synth.pc_batches(2, [100_000, 100_000], d=50)
+    got = bb.queryKNN(X, Q, 20)
+    idx, dist = capi.Kmknn(X).query(Q, 20)
+    assert int((got["index"] != idx).sum()) == 0
+    assert np.array_equal(got["distance"], dist)
+
+
+def test_candidate_scoring_error_is_far_inside_the_certificate_bound():
+    """The tensor-core scores must approximate the exact squared distances much better than the eps the certificate
+    assumes (2^-16 (|q| M + M^2)); otherwise the rescue path would carry the correctness."""
+    import torch
+    from batchelor_b200 import device as dev
+
+    X, Q = synth.pc_batches(2, [20_000, 4_000], d=50)
+    Xd, Qd = torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda()
+    cidx, cd2, thr = dev.debug_candidates(Xd, Qd, 20)
+    cidx, cd2 = cidx.cpu().numpy(), cd2.cpu().numpy()
+    valid = cidx >= 0
+    exact = ((Q[:, None, :] - X[np.where(valid, cidx, 0)]) ** 2).sum(-1)
+    M2 = (X ** 2).sum(1).max(); qn = (Q ** 2).sum(1)
+    eps = 2.0 ** -16 * (np.sqrt(qn * M2) + M2)
+    err = np.abs(cd2 - exact)[valid]
+    ratio = (np.abs(cd2 - exact) / eps[:, None])[valid].max()
+    print(f"max |approx-exact| = {err.max():.3e}, max err/eps = {ratio:.3f}")
+    assert ratio < 0.25
+    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    dev.query_knn(Xd, Qd, 20, stats=stats)
+    s = stats.cpu().numpy()
+    assert s[2] == 1 and s[0] == 0, f"tensor path not taken or queries rescued: {s}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a2 / a3: mutual pairs -- identical lists in the reference's order
+# ---------------------------------------------------------------------------------------------------------------
+def test_find_mutual_nns_matches_golden(golden):
+    g = golden["find_mutual_nns"]
+    first, second = bb.find_mutual_nns(g["w21"], g["w12"])
+    assert np.array_equal(first, g["first"]) and np.array_equal(second, g["second"])
+    res = bb.findMutualNN(g["X1"], g["X2"], k1=10, k2=15)
+    assert np.array_equal(res["first"], g["first"]) and np.array_equal(res["second"], g["second"])
+
+
+@pytest.mark.parametrize("n1,n2,k1,k2", [(3000, 2500, 20, 20), (500, 4000, 5, 30), (64, 64, 64, 64), (1000, 10, 20, 20)])
+def test_find_mutual_nn_matches_oracle(n1, n2, k1, k2):
+    b1, b2 = synth.pc_batches(2, [n1, n2], d=50, ncomp=8)
+    res = bb.findMutualNN(b1, b2, k1=k1, k2=k2)
+    f, s = capi.find_mutual_nn(b1, b2, min(k1, n1), min(k2, n2))
+    assert np.array_equal(res["first"], f) and np.array_equal(res["second"], s)
+    assert np.all(np.diff(res["first"]) >= 0)  # order contract: first ascending
+
+
+def test_find_mutual_nns_empty_and_no_pairs():
+    first, second = bb.find_mutual_nns(np.zeros((0, 3), np.int32), np.ones((4, 2), np.int32))
+    assert first.size == 0 and second.size == 0
+    left = np.array([[1], [1]], np.int32); right = np.array([[2]], np.int32)  # only cell 2 <-> cell 1 is mutual
+    first, second = bb.find_mutual_nns(left, right)
+    assert np.array_equal(first, [2]) and np.array_equal(second, [1])
+    with pytest.raises(bb.B200Error, match="out of range"):
+        bb.find_mutual_nns(np.array([[5]], np.int32), np.array([[1]], np.int32))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a5: Gaussian smoothing; a7: shift variance -- golden vectors from the reference object code + oracle
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["vanilla", "repeated", "many", "wide"])
+def test_smooth_gaussian_kernel_matches_golden(golden, case):
+    g = golden["smooth_gaussian_kernel"]
+    out = bb.smooth_gaussian_kernel(g[f"{case}_averaged"], g[f"{case}_index0"], g["data2"].T, float(g[f"{case}_sigma"]))
+    assert _relerr(out, g[f"{case}_out"]) < 1e-10
+
+
+def test_smooth_gaussian_kernel_more_genes_out_than_in_and_errors():
+    rng = np.random.default_rng(8)
+    mat = rng.normal(scale=0.1, size=(30, 700)); avg = rng.normal(size=(90, 64)); idx = rng.permutation(700)[:64].astype(np.int32)
+    out = bb.smooth_gaussian_kernel(avg, idx, mat, 0.1)   # 'averaged' may cover more genes than 'mat' (:23)
+    assert _relerr(out, capi.smooth_gaussian_kernel(avg, idx, mat, 0.1)) < 1e-10
+    assert np.all(np.isnan(bb.smooth_gaussian_kernel(np.zeros((5, 0)), np.zeros(0, np.int32), mat, 0.1)))
+    with pytest.raises(bb.B200Error, match="out of range"):
+        bb.smooth_gaussian_kernel(avg, idx + 700, mat, 0.1)
+
+
+def test_adjust_shift_variance_matches_golden(golden):
+    g = golden["adjust_shift_variance"]
+    for s in (1.0, 0.1):
+        out = bb.adjust_shift_variance(g["data1"], g["data2"], g["vect"], s, np.arange(400), np.arange(1000))
+        ref = g[f"out_sigma_{s}"]
+        same = np.isclose(out, ref, rtol=1e-9, atol=1e-12)
+        print(f"sigma={s}: identical quantile picks {same.mean():.4f}, max rel err {_relerr(out, ref):.2e}")
+        assert same.mean() >= 0.999   # the discrete pick may flip on a rounding tie (the reference skips platforms over this)
+    out = bb.adjust_shift_variance(g["data1"], g["data2"], g["vect"], 1.0, g["r1"], g["r2"])
+    assert np.isclose(out, g["out_restricted"], rtol=1e-9, atol=1e-12).mean() >= 0.999
+
+
+def test_adjust_shift_variance_restrict_identity_and_zero_vector():  # test-mnn-correct.R:162-173
+    rng = np.random.default_rng(100032)
+    d1 = rng.normal(scale=0.1, size=(25, 120)); d2 = rng.normal(scale=0.1, size=(25, 200)); cv = rng.uniform(size=(200, 25))
+    i1 = np.arange(10, 21); i2 = np.arange(20, 9, -1)
+    A1 = np.hstack([d1, d1[:, i1 - 1]]); A2 = np.hstack([d2, d2[:, i2 - 1]])
+    a = bb.adjust_shift_variance(d1, d2, cv, 1.0, np.arange(120), np.arange(200))
+    b = bb.adjust_shift_variance(A1, A2, np.vstack([cv, cv[i2 - 1]]), 1.0, np.arange(120), np.arange(200))
+    assert np.array_equal(a, b[:200]) and np.array_equal(a[i2 - 1], b[200:])   # expect_identical in the reference
+    cv0 = cv.copy(); cv0[3] = 0.0
+    out = bb.adjust_shift_variance(d1, d2, cv0, 1.0, np.arange(120), np.arange(200))
+    ref = capi.adjust_shift_variance(d1, d2, cv0, 1.0, np.arange(120), np.arange(200))
+    assert not np.isfinite(out[3]) and not np.isfinite(ref[3])   # 0/0 or x/0 kept (:64, :160)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a4 / a6 / a8 / a9 through the host-buffer ABI
+# ---------------------------------------------------------------------------------------------------------------
+def _call_average(t1, m1, t2, m2):
+    import ctypes as C
+    from batchelor_b200 import _lib
+    t1f, t2f = np.asfortranarray(t1), np.asfortranarray(t2)
+    m1 = np.ascontiguousarray(m1, np.int32); m2 = np.ascontiguousarray(m2, np.int32)
+    cap = max(1, min(m1.size, t2.shape[0]))
+    avg = np.zeros(cap * t1.shape[1]); sec = np.zeros(cap, np.int32); n = C.c_int64(0)
+    _lib.call("b200mnn_average_correction", t1f.ctypes.data_as(_lib.f64p), t1.shape[0], t2f.ctypes.data_as(_lib.f64p), t2.shape[0],
+              t1.shape[1], m1.ctypes.data_as(_lib.i32p), m2.ctypes.data_as(_lib.i32p), m1.size, avg.ctypes.data_as(_lib.f64p),
+              sec.ctypes.data_as(_lib.i32p), C.byref(n))
+    return avg[: n.value * t1.shape[1]].reshape((n.value, t1.shape[1]), order="F"), sec[: n.value]
+
+
+def test_average_correction_abi():  # test-fast-mnn.R:6-32
+    rng = np.random.default_rng(1200001)
+    t1 = rng.normal(size=(100, 10)); t2 = rng.normal(size=(200, 10))
+    m1 = rng.integers(1, 101, size=250); m2 = rng.integers(1, 101, size=250)
+    avg, sec = _call_average(t1, m1, t2, m2)
+    ravg, rsec = ho.average_correction(t1, m1, t2, m2)
+    assert np.array_equal(sec, rsec) and _relerr(avg, ravg) < 1e-12
+    avg, sec = _call_average(t1, np.zeros(0, np.int32), t2, np.zeros(0, np.int32))
+    assert avg.shape == (0, 10) and sec.size == 0
+
+
+def test_center_and_tricube_and_cosine_abi():
+    import ctypes as C
+    from batchelor_b200 import _lib
+    rng = np.random.default_rng(1200002)
+    t = np.asfortranarray(rng.normal(size=(100, 10))); b = rng.normal(size=10)
+    out = np.zeros((100, 10), order="F")
+    _lib.call("b200mnn_center_along_batch_vector", t.ctypes.data_as(_lib.f64p), 100, 10, b.ctypes.data_as(_lib.f64p), None, 0, out.ctypes.data_as(_lib.f64p))
+    assert _relerr(out, ho.center_along_batch_vector(t, b)) < 1e-12 and np.std(out @ b) < 1e-8
+    t2 = np.asfortranarray(np.vstack([t, t[:10]])); keep = np.arange(1, 101, dtype=np.int32)
+    out2 = np.zeros((110, 10), order="F")
+    _lib.call("b200mnn_center_along_batch_vector", t2.ctypes.data_as(_lib.f64p), 110, 10, b.ctypes.data_as(_lib.f64p), keep.ctypes.data_as(_lib.i32p), 100, out2.ctypes.data_as(_lib.f64p))
+    assert np.array_equal(out, out2[:100]) and np.array_equal(out2[:10], out2[100:])   # expect_identical (test-fast-mnn.R:43-50)
+
+    corr = np.asfortranarray(rng.normal(size=(50, 10))); involved = (rng.permutation(100)[:50] + 1).astype(np.int32)
+    for k, nd in [(20, 3.0), (11, 3.0), (11, 1.0), (80, 3.0)]:
+        o = np.zeros((100, 10), order="F")
+        _lib.call("b200mnn_tricube_weighted_correction", t.ctypes.data_as(_lib.f64p), 100, 10, corr.ctypes.data_as(_lib.f64p),
+                  involved.ctypes.data_as(_lib.i32p), 50, k, nd, o.ctypes.data_as(_lib.f64p))
+        assert _relerr(o, ho.tricube_weighted_correction(t, corr, involved, k=k, ndist=nd)) < 1e-12
+
+    X = rng.normal(size=(20, 30)); X[:, 4] = 0
+    res = bb.cosineNorm(X, mode="all")
+    m, l2 = capi.cosine_norm(X)
+    assert _relerr(res["matrix"], m) < 1e-14 and _relerr(res["l2norm"], l2) < 1e-14 and np.all(res["matrix"][:, 4] == 0)
+    assert np.allclose(bb.cosineNorm(X, mode="l2norm"), l2)
+    assert np.allclose(bb.cosineNorm(X, subset_row=np.arange(1, 11)), capi.cosine_norm(X[:10])[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole merges: reducedMNN / mnnCorrect against the oracle's restatement of the R loops
+# ---------------------------------------------------------------------------------------------------------------
+def test_reduced_mnn_toy_known_answers():  # tests/testthat/test-reduced-mnn.R:80-105
+    core = np.stack([np.repeat(np.arange(1.0, 11), 10), np.tile(np.arange(1.0, 11), 10)], 1)
+    b1 = core.copy(); b1[:, 0] += 20
+    b2 = core.copy(); b2[:, 1] += 20
+    o1 = bb.reducedMNN(core, b1, k=1).corrected
+    assert np.allclose(o1[:, 0], 5.5) and np.allclose(o1[:, 1], np.r_[core[:, 1], b1[:, 1]])
+    assert np.allclose(bb.reducedMNN(core, b1, b2, k=1).corrected, 5.5)
+    oy = bb.reducedMNN(core + 10, b2 + 10, k=1).corrected
+    assert np.allclose(oy[:, 0], np.r_[core[:, 0], b2[:, 0]] + 10) and np.allclose(oy[:, 1], 15.5)
+    oz = bb.reducedMNN(core, b1, core + 10, b2 + 10, merge_order=[[1, 2], [3, 4]], k=1).corrected
+    assert np.allclose(oz, 5.5)
+
+
+def test_reduced_mnn_matches_oracle_three_batches_and_hierarchy():
+    bs = synth.pc_batches(4, [1500, 1200, 900, 1100], d=50, ncomp=8)
+    for order in (None, [3, 1, 2, 4], [[1, 2], [3, 4]]):
+        got = bb.reducedMNN(*bs, k=20, merge_order=order)
+        ref = ho.reduced_mnn(bs, k=20, merge_order=order)
+        assert np.array_equal(got.batch, ref["batch"])
+        assert got.merge_info["left"] == ref["merge_info"]["left"] and got.merge_info["right"] == ref["merge_info"]["right"]
+        # first merge: identical inputs -> identical pairs; later merges see 1e-16-level input differences
+        assert np.array_equal(got.merge_info["pairs"][0]["left"], ref["merge_info"]["pairs"][0][0])
+        assert np.array_equal(got.merge_info["pairs"][0]["right"], ref["merge_info"]["pairs"][0][1])
+        assert _relerr(got.corrected, ref["corrected"]) < RTOL
+        assert np.allclose(got.merge_info["batch_size"], ref["merge_info"]["batch_size"], rtol=1e-6)
+        assert np.allclose(got.merge_info["lost_var"], ref["merge_info"]["lost_var"], rtol=1e-5, atol=1e-8)
+
+
+def test_reduced_mnn_restrict_propk_batch_and_skip():
+    rng = np.random.default_rng(12000053)
+    B1 = rng.normal(0, size=(300, 10)); B2 = rng.normal(1, size=(400, 10)); B3 = rng.normal(2, size=(200, 10))
+    ref = bb.reducedMNN(B1, B2, B3)
+    i1 = np.arange(100, 49, -1); i2 = np.arange(1, 21); i3 = np.arange(50, 101)
+    C1 = np.vstack([B1, B1[i1 - 1]]); C2 = np.vstack([B2, B2[i2 - 1]]); C3 = np.vstack([B3, B3[i3 - 1]])
+    out = bb.reducedMNN(C1, C2, C3, restrict=[np.arange(1, 301), np.arange(1, 401), np.arange(1, 201)])
+    for b, keep, dup in [(1, 300, i1), (2, 400, i2), (3, 200, i3)]:   # expect_identical in test-reduced-mnn.R:127-135
+        r = ref.corrected[ref.batch == b]; o = out.corrected[out.batch == b]
+        assert np.array_equal(r, o[:keep]) and np.array_equal(r[dup - 1], o[keep:])
+    p1 = bb.reducedMNN(B1, B1 + 1.0, k=10, prop_k=20 / 300); p2 = bb.reducedMNN(B1, B1 + 1.0, k=20)
+    assert np.array_equal(p1.corrected, p2.corrected)   # test-reduced-mnn.R:39-58
+    oracle = ho.reduced_mnn([B1, B2, B3])
+    assert _relerr(ref.corrected, oracle["corrected"]) < RTOL
+    # single matrix + batch factor (R/reducedMNN.R:81-88)
+    allc = np.vstack([B1, B2, B3]); lab = np.r_[np.full(300, 1), np.full(400, 2), np.full(200, 3)]
+    sh = rng.permutation(900)
+    one = bb.reducedMNN(allc[sh], batch=lab[sh])
+    assert _relerr(one.corrected, ref.corrected[sh]) < 1e-12 and np.array_equal(one.batch, lab[sh])
+    # min.batch.skip (test-fast-mnn.R:409-457): no batch effect -> skipped, coordinates unchanged
+    same = bb.reducedMNN(B1, rng.normal(0, size=(350, 10)), min_batch_skip=0.1)
+    assert same.merge_info["skipped"][0] and same.merge_info["batch_size"][0] < 0.1 and np.array_equal(same.corrected[:300], B1)
+
+
+def test_mnn_correct_matches_oracle():
+    A, B, Cc = synth.gene_batches(3, [260, 300, 220], G=120, latent=6, ncomp=4)
+    for kw in (dict(), dict(var_adj=False), dict(cos_norm_in=False, cos_norm_out=False), dict(cos_norm_out=False),
+               dict(merge_order=[3, 1, 2]), dict(sigma=1.0)):
+        got = bb.mnnCorrect(A, B, Cc, k=15, **kw)
+        ref = ho.mnn_correct([A, B, Cc], k=15, **kw)
+        assert np.array_equal(got.batch, ref["batch"])
+        assert np.array_equal(got.merge_info["pairs"][0]["left"], ref["merge_info"]["pairs"][0][0])
+        assert np.array_equal(got.merge_info["pairs"][0]["right"], ref["merge_info"]["pairs"][0][1])
+        err = _relerr(got.corrected, ref["corrected"])
+        print(kw, "rel err", err)
+        assert err < RTOL
+
+
+def test_mnn_correct_restrict_identity():  # test-mnn-correct.R:379-441
+    rng = np.random.default_rng(10004)
+    A = rng.normal(size=(15, 60)); B = rng.normal(size=(15, 80)) + 1
+    ref = bb.mnnCorrect(A, B, k=10)
+    i1 = np.arange(5, 16); i2 = np.arange(20, 9, -1)
+    out = bb.mnnCorrect(np.hstack([A, A[:, i1 - 1]]), np.hstack([B, B[:, i2 - 1]]), k=10, restrict=[np.arange(1, 61), np.arange(1, 81)])
+    r, o = ref.corrected, out.corrected
+    assert np.array_equal(r[:, :60], o[:, :60]) and np.array_equal(r[:, 60:], o[:, 71:151]) and np.array_equal(r[:, 60:][:, i2 - 1], o[:, 151:])
+
+
+def test_results_are_deterministic_run_to_run():
+    b1, b2 = synth.pc_batches(2, [4000, 3500], d=50, ncomp=8)
+    a = bb.reducedMNN(b1, b2, k=20); b = bb.reducedMNN(b1, b2, k=20)
+    assert np.array_equal(a.corrected, b.corrected)
+    assert np.array_equal(a.merge_info["pairs"][0]["left"], b.merge_info["pairs"][0]["left"])
