@@ -26,8 +26,11 @@
 #include <cuda.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 namespace b200 {
 namespace knn {
@@ -56,13 +59,20 @@ struct MmaSched {
     unsigned char b_sub[MAX_NBOX][MAX_MMA_PER_BOX];    // stored slice of B inside the current box (0..3)
 };
 
-// Stored K layout of one operand row (both operands): for every full group g of 16 dims the "hi" slice at
-// 2g and the "lo" slice at 2g+1; then, if r = d % 16 dims remain and 3r <= 16, one packed remainder slice
-//   query row : [qh(r) | qh(r) | ql(r) | 0]      reference row : [xh(r) | xl(r) | xh(r) | 0]
-// whose single MMA yields qh.xh + qh.xl + ql.xh for those dims.  If 3r > 16 the remainder is zero-padded into
-// one more full group.
+// Stored K layout of one operand row (both operands).  With S the common power-of-two scale:
+//   query row     a = -2*S*q  split as a = ah + al (+O(2^-22));     reference row  b = S*x = bh + bl (+O(2^-22))
+// For every full group g of 16 dims the "hi" slice sits at 2g and the "lo" slice at 2g+1 (three MMAs: ah.bh, al.bh,
+// ah.bl).  If r = d % 16 dims remain and 3r <= 16 they are packed into one remainder slice
+//   query row : [ah(r) | ah(r) | al(r) | ...]      reference row : [bh(r) | bl(r) | bh(r) | ...]
+// whose single MMA yields ah.bh + ah.bl + al.bh for those dims (if 3r > 16 the remainder is zero-padded into one more
+// full group).  Three more columns fold the reference norm into the same accumulation:
+//   query row : [2^15, 2^4, 2^-7]                   reference row : N = S^2 ||x||^2 split as 2^15 n1 + 2^4 n2 + 2^-7 n3
+// so the accumulator IS the score S^2 (||x||^2 - 2 q.x): the epilogue needs neither loads nor FMAs.  The norm
+// columns share the remainder slice when 3r + 3 <= 16, else they get a slice (and one MMA) of their own.
 struct KLayout {
     int d, groups, rem, nslices, nbox;
+    int norm_slice, norm_col;   // stored slice and first column (0..13) of the three norm columns
+    int rem_slice;              // stored slice of the packed remainder dims (-1 if none)
 };
 
 static KLayout make_layout(int d) {
@@ -71,7 +81,12 @@ static KLayout make_layout(int d) {
     L.groups = d / SLICE;
     L.rem = d % SLICE;
     if (L.rem * 3 > SLICE) { L.groups += 1; L.rem = 0; }
-    L.nslices = 2 * L.groups + (L.rem ? 1 : 0);
+    int ns = 2 * L.groups;
+    L.rem_slice = -1;
+    if (L.rem) L.rem_slice = ns++;
+    if (L.rem && 3 * L.rem + 3 <= SLICE) { L.norm_slice = L.rem_slice; L.norm_col = 3 * L.rem; }
+    else { L.norm_slice = ns++; L.norm_col = 0; }
+    L.nslices = ns;
     L.nbox = (L.nslices + 3) / 4;
     return L;
 }
@@ -83,14 +98,19 @@ static MmaSched make_sched(const KLayout& L) {
     for (int g = 0; g < L.groups; ++g) {
         const int sh = 2 * g, sl = 2 * g + 1, box = sh / 4;
         int& m = s.nmma[box];
-        s.a_slice[box][m] = (unsigned char)sh; s.b_sub[box][m] = (unsigned char)(sh % 4); ++m;  // qh.xh
-        s.a_slice[box][m] = (unsigned char)sl; s.b_sub[box][m] = (unsigned char)(sh % 4); ++m;  // ql.xh
-        s.a_slice[box][m] = (unsigned char)sh; s.b_sub[box][m] = (unsigned char)(sl % 4); ++m;  // qh.xl
+        s.a_slice[box][m] = (unsigned char)sh; s.b_sub[box][m] = (unsigned char)(sh % 4); ++m;  // ah.bh
+        s.a_slice[box][m] = (unsigned char)sl; s.b_sub[box][m] = (unsigned char)(sh % 4); ++m;  // al.bh
+        s.a_slice[box][m] = (unsigned char)sh; s.b_sub[box][m] = (unsigned char)(sl % 4); ++m;  // ah.bl
     }
-    if (L.rem) {
-        const int sr = 2 * L.groups, box = sr / 4;
+    if (L.rem_slice >= 0) {
+        const int sr = L.rem_slice, box = sr / 4;
         int& m = s.nmma[box];
         s.a_slice[box][m] = (unsigned char)sr; s.b_sub[box][m] = (unsigned char)(sr % 4); ++m;
+    }
+    if (L.norm_slice != L.rem_slice) {
+        const int sn = L.norm_slice, box = sn / 4;
+        int& m = s.nmma[box];
+        s.a_slice[box][m] = (unsigned char)sn; s.b_sub[box][m] = (unsigned char)(sn % 4); ++m;
     }
     return s;
 }
@@ -134,6 +154,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
+// Elects one lane of a fully converged warp (warp-uniform control flow keeps descriptors in uniform registers).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -143,6 +173,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         :
         : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
+}
+// Multicast variant: the box lands at the same CTA-relative shared-memory offset in every CTA of `cta_mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -160,19 +208,26 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, fp32 accumulate, issued by one thread.
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16, fp32 accumulate, issued by one thread.  ACC is a compile-time flag so
+// the issue path carries no predicate arithmetic.
+template <bool ACC>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         :
-        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACC ? 1 : 0)
         : "memory");
 }
 // Arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Same, arriving on the barrier at this offset in every CTA of `cta_mask` (slot recycling under TMA multicast).
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(cta_mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -207,33 +262,188 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 // both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc() { return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
-__device__ __forceinline__ float entry_score(unsigned long long e) { return __uint_as_float((uint32_t)(e >> 32)); }
-__device__ __forceinline__ unsigned long long make_entry(float s, int idx) {
-    return ((unsigned long long)__float_as_uint(s) << 32) | (uint32_t)idx;
+// ------------------------------------------------------------------------------------------------
+// Per-query candidate buffers (epilogue)
+// ------------------------------------------------------------------------------------------------
+// Every query row owns CAP = KEEP + PEND 64-bit keys in shared memory: the KEEP = 32*E best approximate scores seen so
+// far (sorted after the first compaction) followed by up to PEND pending hits.  A key is (order-preserving score bits
+// << 32 | reference id), so unsigned comparison orders by (score, id).  A hit (score < the row's threshold) is appended
+// by the row's own lane with one shared-memory store -- no warp cooperation on the hot path.  When a row is about to
+// run out of room the warp compacts it cooperatively (bitonic sort of the pending keys across lanes, bitonic merge with
+// the retained keys), which also tightens the threshold to the KEEP-th best score.  Thresholds only ever decrease, so
+// every key that was ever rejected or dropped has score >= the final threshold: the certificate of the re-rank kernel.
+constexpr int ROWPITCH = 33;   // buffer position stride (keys): compaction reads of one row are bank-conflict free
+template <int E>
+struct Cand {
+    static constexpr int KEEP = 32 * E;
+    static constexpr int PEND = 32;
+    static constexpr int CAP = KEEP + PEND;
+    static constexpr int WARP_KEYS = CAP * ROWPITCH;
+};
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+
+__device__ __forceinline__ unsigned long long make_key(float s, int col) {
+    uint32_t u = __float_as_uint(s);
+    u ^= (uint32_t)((int32_t)u >> 31) | 0x80000000u;
+    return ((unsigned long long)u << 32) | (uint32_t)col;
+}
+__device__ __forceinline__ float key_score(unsigned long long k) {
+    uint32_t u = (uint32_t)(k >> 32);
+    u ^= ((u >> 31) - 1u) | 0x80000000u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
+
+// bitonic sort of one key per lane, ascending by lane
+__device__ __forceinline__ unsigned long long sort32(unsigned long long key, const int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = ((lane & k) == 0) || (k == 32);      // ascending block?
+            const bool low = (lane & j) == 0;                    // lower partner of the pair?
+            key = (up == low) ? umin64(key, other) : umax64(key, other);
+        }
+    }
+    return key;
+}
+// bitonic sequence (one key per lane) -> ascending
+__device__ __forceinline__ unsigned long long clean32(unsigned long long key, const int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
+        key = ((lane & j) == 0) ? umin64(key, other) : umax64(key, other);
+    }
+    return key;
+}
+__device__ __forceinline__ unsigned long long reverse32(unsigned long long key) { return __shfl_xor_sync(0xffffffffu, key, 31); }
+
+// Compacts every row whose lane has cnt > limit.  buf: this warp's CAP x ROWPITCH keys.
+// (Inlined on purpose: as a call it forced thr/cnt and the live TMEM registers of the caller into local memory.)
+template <int E>
+__device__ __forceinline__ void compact_rows(unsigned long long* __restrict__ buf, const int lane, const int limit, float& thr, int& cnt,
+                                             bool& sorted) {
+    unsigned todo = __ballot_sync(0xffffffffu, cnt > limit);
+    while (todo) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int c = __shfl_sync(0xffffffffu, cnt, r);
+        const bool was_sorted = __shfl_sync(0xffffffffu, (int)sorted, r) != 0;
+        unsigned long long a0 = (lane < c) ? buf[lane * ROWPITCH + r] : EMPTY_KEY;
+        unsigned long long lastkey;
+        if (E == 1) {
+            unsigned long long p = (lane + 32 < c) ? buf[(lane + 32) * ROWPITCH + r] : EMPTY_KEY;
+            if (!was_sorted) a0 = sort32(a0, lane);
+            p = sort32(p, lane);
+            a0 = clean32(umin64(a0, reverse32(p)), lane);          // the 32 smallest of both, sorted
+            buf[lane * ROWPITCH + r] = a0;
+            lastkey = a0;
+        } else {
+            unsigned long long a1 = (lane + 32 < c) ? buf[(lane + 32) * ROWPITCH + r] : EMPTY_KEY;
+            unsigned long long p = (lane + 64 < c) ? buf[(lane + 64) * ROWPITCH + r] : EMPTY_KEY;
+            if (!was_sorted) {
+                a0 = sort32(a0, lane);
+                a1 = sort32(a1, lane);
+                const unsigned long long ra = reverse32(a1);
+                const unsigned long long lo = umin64(a0, ra), hi = umax64(a0, ra);
+                a0 = clean32(lo, lane);
+                a1 = clean32(hi, lane);                             // now a0 <= a1 elementwise, both sorted
+            }
+            p = sort32(p, lane);
+            const unsigned long long lo1 = clean32(umin64(a1, reverse32(p)), lane);   // 32 smallest of (a1 u p); rest dropped
+            const unsigned long long rl = reverse32(lo1);
+            const unsigned long long lo = umin64(a0, rl), hi = umax64(a0, rl);
+            a0 = clean32(lo, lane);
+            a1 = clean32(hi, lane);
+            buf[lane * ROWPITCH + r] = a0;
+            buf[(lane + 32) * ROWPITCH + r] = a1;
+            lastkey = a1;
+        }
+        const int keep = 32 * E;
+        const int newcnt = c < keep ? c : keep;
+        const unsigned long long last = __shfl_sync(0xffffffffu, lastkey, 31);
+        if (lane == r) {
+            cnt = newcnt;
+            sorted = true;
+            thr = (newcnt == keep) ? key_score(last) : __int_as_float(0x7f800000);
+        }
+    }
+    __syncwarp();
+}
+
+// One 32-column chunk of accumulators (registers v[], lane = query row) against this lane's running threshold.
+// Hot path: one min tree and ONE compare/branch per chunk (a single warp per scheduler has no
+// other latency hiding).  Rare path: the lane appends its hits; appends are overflow-safe (a row that fills up
+// remembers where it stopped, gets compacted and resumes with the tightened threshold).
+template <int E>
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const int col0, float& thr, int& cnt, bool& sorted,
+                                             unsigned long long* __restrict__ buf, const int lane) {
+    constexpr int CAP = Cand<E>::CAP;
+    constexpr int SOFT = CAP - 8;
+    float s[32];   // the accumulators ARE the scores (norm and the factor -2 are folded into the MMA)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fminf(fminf(s[4 * j], s[4 * j + 1]), fminf(s[4 * j + 2], s[4 * j + 3]));
+    const float mm = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
+    int ovf_at = 32;
+    if (mm < thr) {  // rare, per lane
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (s[i] < thr) {
+                if (cnt < CAP) {
+                    buf[cnt * ROWPITCH + lane] = make_key(s[i], col0 + i);
+                    ++cnt;
+                } else if (ovf_at == 32) {
+                    ovf_at = i;
+                }
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, (cnt > SOFT) | (ovf_at < 32))) {
+        compact_rows<E>(buf, lane, SOFT, thr, cnt, sorted);
+        if (ovf_at < 32) {  // resume the columns this row could not take (room for PEND >= 32 keys is guaranteed now)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i >= ovf_at && s[i] < thr) {
+                    buf[cnt * ROWPITCH + lane] = make_key(s[i], col0 + i);
+                    ++cnt;
+                }
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2: tensor-core candidate scoring + per-query top-(32*E) of the approximate scores
 // ------------------------------------------------------------------------------------------------
-template <int E>
+template <int E, int NBOX>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float* __restrict__ norms,  // [n_pad] scaled ||x||^2, +inf on padding
                       const MmaSched sched, const int nslot, const int64_t nq, const int ntiles, const int tiles_per_split,
                       int32_t* __restrict__ cand_idx,   // [nsplit][nq][32E]
                       float* __restrict__ cand_score,   // [nsplit][nq][32E] (may be null)
-                      float* __restrict__ thr_out)      // [nsplit][nq]
+                      float* __restrict__ thr_out,      // [nsplit][nq]
+                      const int dbg_mode,               // 0 = normal; 1 = epilogue only recycles stages; 2 = + TMEM loads, no filter
+                      const int csize,                  // thread-block cluster size (1, 2 or 4): CTAs of a cluster share every B box
+                      long long* __restrict__ dbg_ts,   // optional [64][32] clock64 trace of CTA (0,0) (measurement aid)
+                      const int trace_start)            // first tile recorded in the trace
 {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment is what SWIZZLE_128B needs; keeping plain pointer arithmetic on the __shared__ array keeps
+    // the address space visible to the compiler (LDS/STS instead of generic LD/ST in the epilogue).
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nbox = sched.nbox;
+    constexpr int nbox = NBOX;   // boxes (64 fp16 columns) per operand row: compile-time so the MMA issue path unrolls
 
     uint8_t* smA = smem;
     uint8_t* smB = smA + (size_t)nbox * A_BOX_BYTES;
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(smB + (size_t)nslot * B_BOX_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + BM * 32 * E);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + 4 * Cand<E>::WARP_KEYS + 2);
     uint64_t* full = bars;                  // [MAX_SLOTS]
     uint64_t* empty = bars + MAX_SLOTS;     // [MAX_SLOTS]
     uint64_t* afull = bars + 2 * MAX_SLOTS; // [1]
@@ -245,11 +455,17 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int tile1 = min(ntiles, tile0 + tiles_per_split);
     const int my_tiles = tile1 - tile0;
     const int m0 = blockIdx.x * BM;
+    const bool trace = dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#define B200_TS(tile, k)                                                        \
+    do {                                                                        \
+        if (trace && lane == 0 && (tile) >= trace_start && (tile) < trace_start + 64) dbg_ts[((tile) - trace_start) * 32 + (k)] = clock64(); \
+    } while (0)
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < nslot; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+        // a slot is free again once the MMA threads of ALL CTAs of the cluster have retired their reads of it
+        for (int i = 0; i < nslot; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), (uint32_t)csize); }
         mbar_init(smem_u32(afull), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), 4); }
         fence_barrier_init();
@@ -260,8 +476,11 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (csize > 1) cluster_sync_all();   // every CTA's barriers are initialised before any peer multicasts into it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = csize > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -270,132 +489,144 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int b = 0; b < nbox; ++b) tma_load_2d(smem_u32(smA + (size_t)b * A_BOX_BYTES), &tmA, smem_u32(afull), b * KBOX, m0);
             int slot = 0;
             uint32_t phase = 0;
+            const int rows_per = BN / csize;                       // this CTA fetches 1/csize of every box ...
+            const uint32_t part_off = crank * (uint32_t)rows_per * 128u;  // ... and multicasts it to the whole cluster
             for (int t = tile0; t < tile1; ++t) {
                 for (int b = 0; b < nbox; ++b) {
                     mbar_wait(smem_u32(&empty[slot]), phase ^ 1);
+                    if (dbg_mode == 3) {  // measurement aid: no TMA traffic at all, MMAs run on stale shared memory
+                        mbar_arrive(smem_u32(&full[slot]));
+                        if (++slot == nslot) { slot = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(smem_u32(&full[slot]), (uint32_t)B_BOX_BYTES);
-                    tma_load_2d(smem_u32(smB + (size_t)slot * B_BOX_BYTES), &tmB, smem_u32(&full[slot]), b * KBOX, t * BN);
+                    const uint32_t dst = smem_u32(smB + (size_t)slot * B_BOX_BYTES);
+                    if (csize == 1) tma_load_2d(dst, &tmB, smem_u32(&full[slot]), b * KBOX, t * BN);
+                    else tma_load_2d_mc(dst + part_off, &tmB, smem_u32(&full[slot]), b * KBOX, t * BN + (int)crank * rows_per, cmask);
                     if (++slot == nslot) { slot = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // A single thread has no latency hiding, so the per-tile issue path must be straight-line code: every
+        // descriptor of the schedule is precomputed into registers (static indices after unrolling over NBOX x 6).
+        // The whole warp runs the loop (warp-uniform values stay in uniform registers); one elected lane issues.
+        {
             constexpr uint32_t idesc = make_idesc();
+            uint64_t dA[NBOX][MAX_MMA_PER_BOX];
+            uint32_t oB[NBOX][MAX_MMA_PER_BOX];
+            int nm[NBOX];
+            const uint32_t a_base = smem_u32(smA);
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {
+                nm[b] = sched.nmma[b];
+#pragma unroll
+                for (int m = 0; m < MAX_MMA_PER_BOX; ++m) {
+                    const int as = sched.a_slice[b][m];
+                    dA[b][m] = make_sw128_desc(a_base + (uint32_t)(as >> 2) * A_BOX_BYTES + (uint32_t)(as & 3) * 32u);
+                    oB[b][m] = (uint32_t)sched.b_sub[b][m] * 2u;   // 32 bytes per K slice, in the descriptor's 16-byte units
+                }
+            }
+            const uint64_t db_base = make_sw128_desc(smem_u32(smB));
             mbar_wait(smem_u32(afull), 0);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(smA);
-            const uint32_t b_base = smem_u32(smB);
             int slot = 0;
             uint32_t phase = 0;
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int stage = tl & 1;
                 const uint32_t use = (uint32_t)(tl >> 1);
+                B200_TS(tl, 0);
                 mbar_wait(smem_u32(&tempty[stage]), (use & 1) ^ 1);
                 tc_fence_after();
+                B200_TS(tl, 1);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(stage * BN);
-                uint32_t acc = 0;
-                for (int b = 0; b < nbox; ++b) {
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b) {
                     mbar_wait(smem_u32(&full[slot]), phase);
                     tc_fence_after();
-                    const uint32_t b_addr = b_base + (uint32_t)slot * B_BOX_BYTES;
-                    const int nm = sched.nmma[b];
-                    for (int m = 0; m < nm; ++m) {
-                        const int as = sched.a_slice[b][m];
-                        const uint64_t da = make_sw128_desc(a_base + (uint32_t)(as >> 2) * A_BOX_BYTES + (uint32_t)(as & 3) * 32u);
-                        const uint64_t db = make_sw128_desc(b_addr + (uint32_t)sched.b_sub[b][m] * 32u);
-                        umma_f16(tmem_d, da, db, idesc, acc);
-                        acc = 1;
+                    B200_TS(tl, 2 + 2 * (b < 2 ? b : 1));
+                    const uint64_t db0 = db_base + (uint64_t)((uint32_t)slot * (uint32_t)(B_BOX_BYTES >> 4));
+                    if (elect_one()) {
+                        if (dbg_mode != 4) {  // mode 4: TMA pipeline alone (no MMAs issued)
+#pragma unroll
+                            for (int m = 0; m < MAX_MMA_PER_BOX; ++m) {
+                                if (m < nm[b]) {
+                                    if (b == 0 && m == 0) umma_f16<false>(tmem_d, dA[b][m], db0 + oB[b][m], idesc);
+                                    else umma_f16<true>(tmem_d, dA[b][m], db0 + oB[b][m], idesc);
+                                }
+                            }
+                        }
+                        // frees the smem slot (in every CTA of the cluster) once these MMAs retire
+                        if (csize == 1) umma_commit(smem_u32(&empty[slot]));
+                        else umma_commit_mc(smem_u32(&empty[slot]), cmask);
+                        if (b == NBOX - 1) umma_commit(smem_u32(&tfull[stage]));   // accumulator stage complete
                     }
-                    umma_commit(smem_u32(&empty[slot]));  // frees the smem slot once these MMAs retire
+                    __syncwarp();
+                    B200_TS(tl, 3 + 2 * (b < 2 ? b : 1));
                     if (++slot == nslot) { slot = 0; phase ^= 1; }
                 }
-                umma_commit(smem_u32(&tfull[stage]));      // accumulator stage complete
             }
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> threshold filter -> sorted lists =====================
         const int q4 = warp & 3;  // TMEM lane quarter this warp may access
-        unsigned long long* mylist = lists + (size_t)(q4 * 32) * (32 * E);
-        const unsigned long long empty_entry = make_entry(__int_as_float(0x7f800000), -1);
-#pragma unroll 1
-        for (int r = 0; r < 32; ++r)
-#pragma unroll
-            for (int e = 0; e < E; ++e) mylist[(r * E + e) * 32 + lane] = empty_entry;
+        unsigned long long* mybuf = lists + (size_t)(warp - 2) * Cand<E>::WARP_KEYS;   // this warp's candidate buffers
+        int cnt = 0;          // keys currently in this lane's row buffer
+        bool sorted = false;  // retained part sorted (true after the first compaction)
         float thr = __int_as_float(0x7f800000);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int stage = tl & 1;
             const uint32_t use = (uint32_t)(tl >> 1);
+            if (warp == 2) B200_TS(tl, 8);
             mbar_wait(smem_u32(&tfull[stage]), use & 1);
             tc_fence_after();
+            if (warp == 2) B200_TS(tl, 9);
             const int colbase = (tile0 + tl) * BN;
+            const uint32_t tbase = lane_base + (uint32_t)(stage * BN);
+            if (dbg_mode == 1 || dbg_mode == 3 || dbg_mode == 4) {  // measurement aid: pure TMA + MMA pipeline
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                if (warp == 2) B200_TS(tl, 10);
+                continue;
+            }
+            uint32_t va[32], vb[32];
+            tmem_ld32(tbase, va);
+            tmem_ld_wait();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + (uint32_t)(stage * BN + c * 32), v);
+            for (int c = 0; c < BN / 32; c += 2) {
+                tmem_ld32(tbase + (uint32_t)((c + 1) * 32), vb);   // in flight while chunk c is filtered
+                if (trace && warp == 2 && tl >= trace_start && tl < trace_start + 64 && c == 0) {
+                    const int tot = __reduce_add_sync(0xffffffffu, cnt);
+                    if (lane == 0) dbg_ts[(tl - trace_start) * 32 + 24] = tot;
+                }
+                if (dbg_mode != 2) filter_chunk<E>(va, colbase + c * 32, thr, cnt, sorted, mybuf, lane);
+                if (warp == 2) B200_TS(tl, 16 + c);
+                else if (__uint_as_float(va[0]) == 1.2345e-30f && __uint_as_float(va[31]) == 1.2345e-30f) thr = 0.f;
                 tmem_ld_wait();
-                if (c == BN / 32 - 1) {  // every column of this stage is now in registers: hand it back to the MMA warp
+                if (c + 2 < BN / 32) {
+                    tmem_ld32(tbase + (uint32_t)((c + 2) * 32), va);
+                } else {  // every column of this stage is now in registers: hand the stage back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                    if (warp == 2) B200_TS(tl, 10);
                 }
-                const float4* np4 = reinterpret_cast<const float4*>(norms + colbase + c * 32);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4 na = __ldg(np4 + 2 * g), nb = __ldg(np4 + 2 * g + 1);
-                    float s[8];
-                    s[0] = fmaf(__uint_as_float(v[8 * g + 0]), -2.f, na.x);
-                    s[1] = fmaf(__uint_as_float(v[8 * g + 1]), -2.f, na.y);
-                    s[2] = fmaf(__uint_as_float(v[8 * g + 2]), -2.f, na.z);
-                    s[3] = fmaf(__uint_as_float(v[8 * g + 3]), -2.f, na.w);
-                    s[4] = fmaf(__uint_as_float(v[8 * g + 4]), -2.f, nb.x);
-                    s[5] = fmaf(__uint_as_float(v[8 * g + 5]), -2.f, nb.y);
-                    s[6] = fmaf(__uint_as_float(v[8 * g + 6]), -2.f, nb.z);
-                    s[7] = fmaf(__uint_as_float(v[8 * g + 7]), -2.f, nb.w);
-                    const bool hit = (s[0] < thr) | (s[1] < thr) | (s[2] < thr) | (s[3] < thr) | (s[4] < thr) | (s[5] < thr) |
-                                     (s[6] < thr) | (s[7] < thr);
-                    if (__any_sync(0xffffffffu, hit)) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            unsigned ballot = __ballot_sync(0xffffffffu, s[i] < thr);
-                            const int col = colbase + c * 32 + g * 8 + i;
-                            while (ballot) {  // warp-uniform: one cooperative insertion per hitting row
-                                const int r = __ffs(ballot) - 1;
-                                ballot &= ballot - 1;
-                                const float sr = __shfl_sync(0xffffffffu, s[i], r);
-                                const unsigned long long ne = make_entry(sr, col);
-                                float newthr;
-                                if (E == 1) {
-                                    const unsigned long long cur = mylist[r * 32 + lane];
-                                    const bool gt = entry_score(cur) > sr;
-                                    const unsigned long long up = __shfl_up_sync(0xffffffffu, cur, 1);
-                                    const int pos = __ffs(__ballot_sync(0xffffffffu, gt)) - 1;
-                                    const unsigned long long nw = lane < pos ? cur : (lane == pos ? ne : up);
-                                    mylist[r * 32 + lane] = nw;
-                                    newthr = entry_score(__shfl_sync(0xffffffffu, nw, 31));
-                                } else {
-                                    const unsigned long long a = mylist[(r * 2 + 0) * 32 + lane];  // sorted position 2*lane
-                                    const unsigned long long b = mylist[(r * 2 + 1) * 32 + lane];  // sorted position 2*lane+1
-                                    const bool ga = entry_score(a) > sr, gb = entry_score(b) > sr;
-                                    const unsigned long long pb = __shfl_up_sync(0xffffffffu, b, 1);
-                                    const bool gp = lane > 0 && entry_score(pb) > sr;
-                                    const unsigned long long na2 = !ga ? a : (gp ? pb : ne);
-                                    const unsigned long long nb2 = !gb ? b : (ga ? a : ne);
-                                    mylist[(r * 2 + 0) * 32 + lane] = na2;
-                                    mylist[(r * 2 + 1) * 32 + lane] = nb2;
-                                    newthr = entry_score(__shfl_sync(0xffffffffu, nb2, 31));
-                                }
-                                if (lane == r) thr = newthr;
-                            }
-                        }
-                    }
-                }
+                if (dbg_mode != 2) filter_chunk<E>(vb, colbase + (c + 1) * 32, thr, cnt, sorted, mybuf, lane);
+                if (warp == 2) B200_TS(tl, 17 + c);
+                else if (__uint_as_float(vb[0]) == 1.2345e-30f && __uint_as_float(vb[31]) == 1.2345e-30f) thr = 0.f;
+                tmem_ld_wait();
+            }
+            if (warp == 2) B200_TS(tl, 11);
+            if (trace && warp == 2 && tl >= trace_start && tl < trace_start + 64) {
+                const int tot = __reduce_add_sync(0xffffffffu, cnt);
+                if (lane == 0) dbg_ts[(tl - trace_start) * 32 + 25] = tot;
             }
         }
-        // write the retained candidates: row r of this warp, 32*E entries, coalesced
+        // final compaction of every row, then write the retained candidates: row r, 32*E entries, coalesced
+        compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);
         const int64_t rowbase = (int64_t)m0 + q4 * 32;
         const int64_t sbase = (int64_t)blockIdx.y * nq;
 #pragma unroll 1
@@ -404,10 +635,10 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (row < nq) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    const unsigned long long en = mylist[(r * E + e) * 32 + lane];
-                    const int64_t o = (sbase + row) * (32 * E) + (E == 1 ? lane : lane * 2 + e);
-                    cand_idx[o] = (int32_t)(uint32_t)en;
-                    if (cand_score) cand_score[o] = entry_score(en);
+                    const unsigned long long key = mybuf[(lane + 32 * e) * ROWPITCH + r];
+                    const int64_t o = (sbase + row) * (32 * E) + lane + 32 * e;
+                    cand_idx[o] = (int32_t)(uint32_t)key;       // EMPTY_KEY -> -1
+                    if (cand_score) cand_score[o] = key_score(key);
                 }
             }
         }
@@ -415,6 +646,7 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tc_fence_before();
     }
     __syncthreads();
+    if (csize > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -422,29 +654,54 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: absmax of an fp64 array (non-negative floats order like their bit patterns)
+// K0: row statistics.  One thread per row: squared norm in double (dimension order, unfused -- the same value the
+// reference arithmetic would produce), plus the global max |x| and max ||x||^2 (non-negative IEEE values order like
+// their bit patterns, so integer atomicMax does it).
 // ------------------------------------------------------------------------------------------------
-__global__ void absmax_kernel(const double* __restrict__ x, int64_t count, unsigned int* __restrict__ out_bits) {
-    float m = 0.f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
-        const float a = fabsf((float)x[i]);
-        m = (a > m) ? a : m;  // NaN never wins
+__global__ void rowstat_kernel(const double* __restrict__ X, int64_t n, int d, double* __restrict__ norm_f64,
+                               unsigned int* __restrict__ absmax_bits, unsigned long long* __restrict__ maxnorm_bits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float am = 0.f;
+    double nrm = 0.0;
+    if (i < n) {
+        const double* x = X + i * d;
+        for (int t = 0; t < d; ++t) {
+            const double xv = x[t];
+            nrm = __dadd_rn(nrm, __dmul_rn(xv, xv));
+            const float a = fabsf((float)xv);
+            am = (a > am) ? a : am;  // NaN never wins
+        }
+        norm_f64[i] = nrm;
     }
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) {
-        // round up one ulp so the double value can never exceed it
-        atomicMax(out_bits, __float_as_uint(m) + 1u);
+    unsigned long long nb = (nrm >= 0.0) ? (unsigned long long)__double_as_longlong(nrm) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, nb, o);
+        nb = ob > nb ? ob : nb;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (am > 0.f) atomicMax(absmax_bits, __float_as_uint(am) + 1u);  // +1 ulp: never below the double value
+        if (maxnorm_bits) atomicMax(maxnorm_bits, nb);
     }
 }
 
-// scale exponent e such that |x| * 2^e < 2^15 for all x; stored as int
-__global__ void scale_kernel(const unsigned int* __restrict__ absmax_bits, int* __restrict__ scale_exp) {
+// Scale exponent e (S = 2^e) such that |2 S x| < 2^13 for every element (fp16 range with headroom, low parts stay
+// normal) and S^2 ||x||^2 < 2^30 for every reference row (so N / 2^15 fits fp16).
+__global__ void scale_kernel(const unsigned int* __restrict__ absmax_bits, const unsigned long long* __restrict__ maxnorm_bits,
+                             int* __restrict__ scale_exp) {
     const float m = __uint_as_float(*absmax_bits);
     int e = 0;
     if (m > 0.f && isfinite(m)) {
         int ex;
-        frexpf(m, &ex);  // m = f * 2^ex, f in [0.5, 1)  =>  m < 2^ex
-        e = 15 - ex;
+        frexpf(m, &ex);  // m < 2^ex
+        e = 12 - ex;
+        const double mn = sqrt(__longlong_as_double((long long)*maxnorm_bits)) * 1.0000001;
+        if (mn > 0.0 && isfinite(mn)) {
+            int en;
+            frexp(mn, &en);  // ||x|| < 2^en
+            e = min(e, 15 - en);
+        }
     }
     *scale_exp = e;
 }
@@ -459,29 +716,35 @@ __device__ __forceinline__ void split_half(double xs, __half& hi, __half& lo) {
 
 template <bool IS_QUERY>
 __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int64_t n_pad, int d, KLayout L,
-                                    const int* __restrict__ scale_exp, __half* __restrict__ op, float* __restrict__ norm_f32,
-                                    double* __restrict__ norm_f64, unsigned long long* __restrict__ maxnorm_bits) {
+                                    const int* __restrict__ scale_exp, __half* __restrict__ op, const double* __restrict__ norm_f64) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     const int KS = L.nbox * KBOX;
     uint4* row = reinterpret_cast<uint4*>(op + i * KS);
+    __align__(16) __half hbuf[16];
+    __align__(16) __half lbuf[16];
     if (i >= n) {
+        // padding: zero operand; a padded REFERENCE row gets an infinite norm so that it never becomes a candidate
         for (int c = 0; c < KS / 8; ++c) row[c] = make_uint4(0, 0, 0, 0);
-        if (norm_f32) norm_f32[i] = __int_as_float(0x7f800000);
+        if (!IS_QUERY) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hbuf[j] = __float2half(0.f);
+            hbuf[L.norm_col] = __ushort_as_half((unsigned short)0x7C00);  // +inf
+            const uint4* hp = reinterpret_cast<const uint4*>(hbuf);
+            row[L.norm_slice * 2 + 0] = hp[0];
+            row[L.norm_slice * 2 + 1] = hp[1];
+        }
         return;
     }
     const double S = scalbn(1.0, *scale_exp);
+    const double mul = IS_QUERY ? -2.0 * S : S;
     const double* x = X + i * d;
-    double nrm = 0.0;
-    __align__(16) __half hbuf[16];
-    __align__(16) __half lbuf[16];
     for (int g = 0; g < L.groups; ++g) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int t = g * 16 + j;
             const double xv = (t < d) ? x[t] : 0.0;
-            nrm = __dadd_rn(nrm, __dmul_rn(xv, xv));
-            split_half(xv * S, hbuf[j], lbuf[j]);
+            split_half(xv * mul, hbuf[j], lbuf[j]);
         }
         const uint4* hp = reinterpret_cast<const uint4*>(hbuf);
         const uint4* lp = reinterpret_cast<const uint4*>(lbuf);
@@ -490,38 +753,48 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
         row[(2 * g + 1) * 2 + 0] = lp[0];
         row[(2 * g + 1) * 2 + 1] = lp[1];
     }
+    // norm columns: constants on the query side, the split scaled norm on the reference side
+    __half nc[3];
+    if (IS_QUERY) {
+        nc[0] = __float2half(32768.f);      // 2^15
+        nc[1] = __float2half(16.f);         // 2^4
+        nc[2] = __float2half(0.0078125f);   // 2^-7
+    } else {
+        const double N = norm_f64[i] * S * S;
+        nc[0] = __double2half(N * 0.000030517578125);                           // N / 2^15
+        const double r1 = N - (double)__half2float(nc[0]) * 32768.0;
+        nc[1] = __double2half(r1 * 0.0625);                                     // r1 / 2^4
+        const double r2 = r1 - (double)__half2float(nc[1]) * 16.0;
+        nc[2] = __double2half(r2 * 128.0);                                      // r2 / 2^-7
+    }
     int written = 2 * L.groups;
-    if (L.rem) {
+    if (L.rem_slice >= 0) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) hbuf[j] = __float2half(0.f);
         const int r = L.rem;
         for (int j = 0; j < r; ++j) {
-            const double xv = x[L.groups * 16 + j];
-            nrm = __dadd_rn(nrm, __dmul_rn(xv, xv));
             __half h, l;
-            split_half(xv * S, h, l);
+            split_half(x[L.groups * 16 + j] * mul, h, l);
             hbuf[j] = h;
             if (IS_QUERY) { hbuf[r + j] = h; hbuf[2 * r + j] = l; }
             else          { hbuf[r + j] = l; hbuf[2 * r + j] = h; }
         }
+        if (L.norm_slice == L.rem_slice) { hbuf[L.norm_col] = nc[0]; hbuf[L.norm_col + 1] = nc[1]; hbuf[L.norm_col + 2] = nc[2]; }
         const uint4* hp = reinterpret_cast<const uint4*>(hbuf);
         row[written * 2 + 0] = hp[0];
         row[written * 2 + 1] = hp[1];
         ++written;
     }
-    for (int s = written; s < L.nbox * 4; ++s) { row[s * 2 + 0] = make_uint4(0, 0, 0, 0); row[s * 2 + 1] = make_uint4(0, 0, 0, 0); }
-    if (norm_f32) norm_f32[i] = (float)(nrm * S * S);
-    if (norm_f64) norm_f64[i] = nrm;
-    if (maxnorm_bits) {
-        // warp-aggregate then one atomic (non-negative doubles order like their bit patterns)
-        unsigned long long b = (unsigned long long)__double_as_longlong(nrm);
-        if (!(nrm >= 0.0)) b = 0;  // NaN
-        for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long ob = __shfl_xor_sync(__activemask(), b, o);
-            b = ob > b ? ob : b;
-        }
-        if ((threadIdx.x & 31) == 0) atomicMax(maxnorm_bits, b);
+    if (L.norm_slice != L.rem_slice) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hbuf[j] = __float2half(0.f);
+        hbuf[0] = nc[0]; hbuf[1] = nc[1]; hbuf[2] = nc[2];
+        const uint4* hp = reinterpret_cast<const uint4*>(hbuf);
+        row[written * 2 + 0] = hp[0];
+        row[written * 2 + 1] = hp[1];
+        ++written;
     }
+    for (int sl = written; sl < L.nbox * 4; ++sl) { row[sl * 2 + 0] = make_uint4(0, 0, 0, 0); row[sl * 2 + 1] = make_uint4(0, 0, 0, 0); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -755,7 +1028,7 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 }
 
 static size_t candidates_smem_bytes(int nbox, int nslot, int E) {
-    return 1024 /* alignment slack */ + (size_t)nbox * A_BOX_BYTES + (size_t)nslot * B_BOX_BYTES + (size_t)BM * 32 * E * 8 +
+    return 1024 /* alignment slack */ + (size_t)nbox * A_BOX_BYTES + (size_t)nslot * B_BOX_BYTES + (size_t)(4 * (32 * E + 32) * ROWPITCH + 2) * 8 +
            (2 * MAX_SLOTS + 5) * 8 + 16;
 }
 
@@ -763,7 +1036,41 @@ bool tensor_path_supported(int64_t n, int64_t nq, int d, int k) {
     if (d < 1 || k < 1 || n < 1 || nq < 1) return false;
     if (k > MAX_K_TENSOR) return false;
     if (n > (int64_t)INT32_MAX - 512 || nq > (int64_t)INT32_MAX - 512) return false;
-    return make_layout(d).nbox <= MAX_NBOX;
+    const KLayout L = make_layout(d);
+    if (L.nbox > MAX_NBOX) return false;
+    // the resident query operand, the candidate buffers and at least three reference boxes must fit in 227 KB
+    return candidates_smem_bytes(L.nbox, 3, k <= 24 ? 1 : 2) <= (size_t)232448;
+}
+
+// Optional timing of the dominant kernel (bench.py's roofline figure): CUDA events recorded on the launch stream
+// around every knn_candidates_kernel launch while enabled; collected (and synchronised) on demand.
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static double g_prof_flops = 0.0;
+
+int profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    for (auto& e : g_prof_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    g_prof_events.clear();
+    g_prof_flops = 0.0;
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int profile_collect(double* total_ms, int64_t* launches, double* flops) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    double ms = 0.0;
+    for (auto& e : g_prof_events) {
+        B200_CUDA(cudaEventSynchronize(e.second));
+        float t = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&t, e.first, e.second));
+        ms += t;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int64_t)g_prof_events.size();
+    if (flops) *flops = g_prof_flops;
+    return 0;
 }
 
 struct DebugOut {
@@ -808,7 +1115,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
 
     __half* opB = ws.get<__half>((size_t)n_pad * KS);
     __half* opA = ws.get<__half>((size_t)nq_pad * KS);
-    float* norms = ws.get<float>((size_t)n_pad);
+    double* xnorm = ws.get<double>((size_t)n_pad);
     double* qnorm = ws.get<double>((size_t)nq_pad);
     int32_t* cand_idx = ws.get<int32_t>((size_t)nsplit * nq * per);
     float* cand_score = dbg ? ws.get<float>((size_t)nsplit * nq * per) : nullptr;
@@ -822,40 +1129,109 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     int* flag_count = reinterpret_cast<int*>(scalars + 24);
     B200_CUDA(cudaMemsetAsync(scalars, 0, 64, stream));
 
-    {
-        const int blocks = sm_count() * 8;
-        absmax_kernel<<<blocks, 256, 0, stream>>>(dX, n * d, absmax_bits);
-        B200_LAUNCH_CHECK();
-        absmax_kernel<<<blocks, 256, 0, stream>>>(dQ, nq * d, absmax_bits);
-        B200_LAUNCH_CHECK();
-        scale_kernel<<<1, 1, 0, stream>>>(absmax_bits, scale_exp);
-        B200_LAUNCH_CHECK();
-        prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, norms, nullptr, maxnorm_bits);
-        B200_LAUNCH_CHECK();
-        prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr, qnorm, nullptr);
-        B200_LAUNCH_CHECK();
-    }
+    rowstat_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(dX, n, d, xnorm, absmax_bits, maxnorm_bits);
+    B200_LAUNCH_CHECK();
+    rowstat_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, stream>>>(dQ, nq, d, qnorm, absmax_bits, nullptr);
+    B200_LAUNCH_CHECK();
+    scale_kernel<<<1, 1, 0, stream>>>(absmax_bits, maxnorm_bits, scale_exp);
+    B200_LAUNCH_CHECK();
+    prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm);
+    B200_LAUNCH_CHECK();
+    prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr);
+    B200_LAUNCH_CHECK();
 
+    // Thread-block clusters: the CTAs of a cluster work on different query tiles against the SAME stream of reference
+    // boxes; each CTA fetches 1/csize of every box and TMA-multicasts it, which divides the L2->SM traffic (the
+    // limiter of the unclustered kernel: 64 KB per tile per SM = 6 TB/s chip-wide) by csize.
+    int csize = mtiles >= 8 ? 4 : (mtiles >= 2 ? 2 : 1);
+    if (const char* ce = getenv("B200MNN_CLUSTER")) {
+        const int c = atoi(ce);
+        if (c == 1 || c == 2 || c == 4) csize = c;
+    }
     CUtensorMap tmA, tmB;
     B200_TRY(make_operand_map(&tmA, opA, nq_pad, KS, BM));
-    B200_TRY(make_operand_map(&tmB, opB, n_pad, KS, BN));
+    B200_TRY(make_operand_map(&tmB, opB, n_pad, KS, BN / csize));
 
     int dev = 0, max_smem = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int nslot = MAX_SLOTS;
-    while (nslot > 2 && candidates_smem_bytes(L.nbox, nslot, E) > (size_t)max_smem) --nslot;
+    while (nslot > 3 && candidates_smem_bytes(L.nbox, nslot, E) > (size_t)max_smem) --nslot;
     const size_t smem = candidates_smem_bytes(L.nbox, nslot, E);
     if (smem > (size_t)max_smem) return fail(B200MNN_ECUDA, "device does not offer enough shared memory per block for the kNN kernel");
-    dim3 grid((unsigned)mtiles, (unsigned)nsplit);
-    if (E == 1) {
-        B200_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_candidates_kernel<1><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, norms, sched, nslot, nq, ntiles, tiles_per_split, cand_idx, cand_score, thr);
-    } else {
-        B200_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        knn_candidates_kernel<2><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, norms, sched, nslot, nq, ntiles, tiles_per_split, cand_idx, cand_score, thr);
+    const char* dbg_env = getenv("B200MNN_DEBUG_MODE");   // measurement aid only (results are wrong when non-zero)
+    const int dbg_mode = dbg_env ? atoi(dbg_env) : 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        if (g_prof_on) {
+            B200_CUDA(cudaEventCreate(&ev0));
+            B200_CUDA(cudaEventCreate(&ev1));
+            B200_CUDA(cudaEventRecord(ev0, stream));
+        }
     }
+    long long* dbg_ts = nullptr;
+    const int trace_start = getenv("B200MNN_TRACE") ? atoi(getenv("B200MNN_TRACE")) : 0;
+    if (getenv("B200MNN_TRACE")) {  // measurement aid: per-tile clock64 trace of CTA (0,0), printed after the launch
+        dbg_ts = ws.get<long long>(64 * 32);
+        if (!dbg_ts) return B200MNN_ENOMEM;
+        B200_CUDA(cudaMemsetAsync(dbg_ts, 0, sizeof(long long) * 64 * 32, stream));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)round_up(mtiles, csize), (unsigned)nsplit, 1);   // padding CTAs see only zero-filled query rows
+    cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int64_t nq_c = nq;
+#define B200_LAUNCH_CAND(EE, NB)                                                                                              \
+    do {                                                                                                                       \
+        B200_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<EE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_kernel<EE, NB>, tmA, tmB, sched, nslot, nq_c, ntiles,                 \
+                                     tiles_per_split, cand_idx, cand_score, thr, dbg_mode, csize, dbg_ts, trace_start));       \
+    } while (0)
+#define B200_LAUNCH_CAND_E(NB)               \
+    do {                                     \
+        if (E == 1) B200_LAUNCH_CAND(1, NB); \
+        else B200_LAUNCH_CAND(2, NB);        \
+    } while (0)
+    switch (L.nbox) {
+        case 1: B200_LAUNCH_CAND_E(1); break;
+        case 2: B200_LAUNCH_CAND_E(2); break;
+        case 3: B200_LAUNCH_CAND_E(3); break;
+        case 4: B200_LAUNCH_CAND_E(4); break;
+        case 5: B200_LAUNCH_CAND_E(5); break;
+        default: B200_LAUNCH_CAND_E(6); break;
+    }
+#undef B200_LAUNCH_CAND_E
+#undef B200_LAUNCH_CAND
     B200_LAUNCH_CHECK();
+    if (dbg_ts) {
+        static long long h[64 * 32];
+        B200_CUDA(cudaMemcpyAsync(h, dbg_ts, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        B200_CUDA(cudaStreamSynchronize(stream));
+        const long long t00 = h[0];
+        fprintf(stderr, "tile: mma[wait_tempty got_tempty got_full0 issued0 got_full1 issued1] epi[wait_tfull got_tfull released done] (cycles rel.)\n");
+        for (int t = 0; t < 24; ++t) {
+            fprintf(stderr, "%5d:", t + trace_start);
+            for (int k2 = 0; k2 < 12; ++k2) if (k2 < 6 || k2 >= 8) fprintf(stderr, " %7lld", h[t * 32 + k2] ? h[t * 32 + k2] - t00 : -1LL);
+            fprintf(stderr, "  chunks:");
+            for (int k2 = 16; k2 < 24; ++k2) fprintf(stderr, " %5lld", h[t * 32 + k2] ? h[t * 32 + k2] - h[t * 32 + 9] : -1LL);
+            fprintf(stderr, " cnt0=%lld cnt1=%lld\n", h[t * 32 + 24], h[t * 32 + 25]);
+        }
+    }
+    if (ev0) {
+        B200_CUDA(cudaEventRecord(ev1, stream));
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        g_prof_events.emplace_back(ev0, ev1);
+        g_prof_flops += 2.0 * (double)nq * (double)n * (double)d;
+    }
 
     if (dbg) {
         const int64_t ncand = (int64_t)nsplit * per;
@@ -881,6 +1257,12 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
 }  // namespace b200
 
 extern "C" {
+
+int b200mnn_profile_enable(int on) { return b200::knn::profile_enable(on); }
+
+int b200mnn_profile_collect(double* total_ms, int64_t* launches, double* algorithmic_flops) {
+    return b200::knn::profile_collect(total_ms, launches, algorithmic_flops);
+}
 
 int b200mnn_dev_query_knn(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
                           int64_t* d_stats, void* stream) {

@@ -171,6 +171,13 @@ int b200mnn_dev_debug_candidates(const double* dX, int64_t n, const double* dQ, 
                                  int32_t* d_cand_idx, double* d_cand_d2, double* d_thr, int64_t cand_capacity,
                                  int64_t* ncand_out, void* stream);
 
+/* Measurement hook (bench.py's roofline figure): while enabled, CUDA events are recorded on the launch stream around
+ * every launch of the dominant kernel (the tcgen05 candidate-scoring kernel).  b200mnn_profile_collect synchronises
+ * those events and returns their summed duration, the number of launches and the ALGORITHMIC flops (2*nq*n*d per
+ * launch) they covered.  b200mnn_profile_enable(x) also clears earlier records. */
+int b200mnn_profile_enable(int on);
+int b200mnn_profile_collect(double* total_ms, int64_t* launches, double* algorithmic_flops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -305,8 +305,13 @@ def test_reduced_mnn_restrict_propk_batch_and_skip():
     one = bb.reducedMNN(allc[sh], batch=lab[sh])
     assert _relerr(one.corrected, ref.corrected[sh]) < 1e-12 and np.array_equal(one.batch, lab[sh])
     # min.batch.skip (test-fast-mnn.R:409-457): no batch effect -> skipped, coordinates unchanged
-    same = bb.reducedMNN(B1, rng.normal(0, size=(350, 10)), min_batch_skip=0.1)
-    assert same.merge_info["skipped"][0] and same.merge_info["batch_size"][0] < 0.1 and np.array_equal(same.corrected[:300], B1)
+    nob = rng.normal(0, size=(350, 10))
+    same = bb.reducedMNN(B1, nob, min_batch_skip=0.5)
+    want = ho.reduced_mnn([B1, nob], min_batch_skip=0.5)
+    assert same.merge_info["skipped"][0] and want["merge_info"]["skipped"][0]
+    assert np.isclose(same.merge_info["batch_size"][0], want["merge_info"]["batch_size"][0], rtol=1e-9) and same.merge_info["batch_size"][0] < 0.5
+    assert np.array_equal(same.corrected[:300], B1) and np.array_equal(same.corrected[300:], nob)
+    assert bb.reducedMNN(B1, B2, min_batch_skip=0.5).merge_info["batch_size"][0] > 0.5   # a real offset is not skipped
 
 
 def test_mnn_correct_matches_oracle():
