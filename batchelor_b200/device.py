@@ -78,22 +78,35 @@ def query_knn_sharded(X: torch.Tensor, Q: torch.Tensor, k: int, want_dist: bool 
 
     if not (dist_.is_available() and dist_.is_initialized()) or dist_.get_world_size() == 1:
         return query_knn(X, Q, k, want_dist)
-    ws, rank = dist_.get_world_size(), dist_.get_rank()
-    nq = Q.shape[0]
-    if nq < ws * min_rows_per_rank:
+    if Q.shape[0] < dist_.get_world_size() * min_rows_per_rank:
         return query_knn(X, Q, k, want_dist)
-    per = (nq + ws - 1) // ws
-    lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
-    idx_l, dist_l = query_knn(X, Q[lo:hi], k, want_dist)
-    idx_pad = torch.zeros((per, k), dtype=torch.int32, device=X.device)
+    return shard_rows_and_gather(Q.shape[0], k, lambda lo, hi: query_knn(X, Q[lo:hi], k, want_dist), X.device, want_dist)
+
+
+def shard_bounds(nq: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """Contiguous block of query rows owned by `rank`: (lo, hi, rows_per_rank)."""
+    per = (nq + world - 1) // world
+    return min(nq, rank * per), min(nq, (rank + 1) * per), per
+
+
+def shard_rows_and_gather(nq: int, k: int, compute_local, device, want_dist: bool = True):
+    """Host-side sharding logic (backend-agnostic: NCCL on GPUs, gloo in the CPU tests): every rank computes
+    `compute_local(lo, hi) -> (idx[hi-lo, k], dist or None)` for its block of rows; blocks are padded to equal size and
+    all-gathered so every rank ends with the full [nq, k] result in row order."""
+    import torch.distributed as dist_
+
+    ws, rank = dist_.get_world_size(), dist_.get_rank()
+    lo, hi, per = shard_bounds(nq, ws, rank)
+    idx_l, dist_l = compute_local(lo, hi)
+    idx_pad = torch.zeros((per, k), dtype=torch.int32, device=device)
     idx_pad[: hi - lo] = idx_l
-    idx_all = torch.empty((ws * per, k), dtype=torch.int32, device=X.device)
+    idx_all = torch.empty((ws * per, k), dtype=torch.int32, device=device)
     dist_.all_gather_into_tensor(idx_all, idx_pad)
     dist_all = None
     if want_dist:
-        d_pad = torch.zeros((per, k), dtype=torch.float64, device=X.device)
+        d_pad = torch.zeros((per, k), dtype=torch.float64, device=device)
         d_pad[: hi - lo] = dist_l
-        dist_all = torch.empty((ws * per, k), dtype=torch.float64, device=X.device)
+        dist_all = torch.empty((ws * per, k), dtype=torch.float64, device=device)
         dist_.all_gather_into_tensor(dist_all, d_pad)
         dist_all = dist_all[:nq]
     return idx_all[:nq], dist_all

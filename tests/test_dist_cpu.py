@@ -1,0 +1,62 @@
+"""World-size-2 `gloo` test (CPU) of the multi-GPU host logic: query rows are sharded into contiguous blocks, each rank
+computes its block, padded blocks are all-gathered and every rank ends with the full result in row order.  On GPUs the
+same function runs over NCCL with the CUDA kNN as `compute_local`; here `compute_local` is the CPU oracle (tests may use it)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nq, k, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from batchelor_b200 import device as dev, synth
+    from oracle import capi
+
+    X, Q = synth.pc_batches(2, [700, nq], d=12, ncomp=4)
+
+    def compute_local(lo, hi):
+        if hi <= lo:
+            return torch.zeros((0, k), dtype=torch.int32), torch.zeros((0, k), dtype=torch.float64)
+        idx, d = capi.query_knn(X, Q[lo:hi], k, nthreads=1)
+        return torch.from_numpy(np.ascontiguousarray(idx - 1)), torch.from_numpy(np.ascontiguousarray(d))
+
+    idx, d = dev.shard_rows_and_gather(nq, k, compute_local, torch.device("cpu"), want_dist=True)
+    np.save(os.path.join(out_dir, f"idx_{rank}.npy"), idx.numpy())
+    np.save(os.path.join(out_dir, f"dist_{rank}.npy"), d.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [501, 2, 1])   # ragged split, fewer rows than ranks
+def test_query_sharding_world_size_2_gloo(tmp_path, nq):
+    from batchelor_b200 import device as dev, synth
+    from oracle import capi
+
+    k, world = 5, 2
+    mp.spawn(_worker, args=(world, _free_port(), nq, k, str(tmp_path)), nprocs=world, join=True)
+    X, Q = synth.pc_batches(2, [700, nq], d=12, ncomp=4)
+    want_idx, want_d = capi.query_knn(X, Q, k)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"idx_{r}.npy"), want_idx - 1)
+        assert np.array_equal(np.load(tmp_path / f"dist_{r}.npy"), want_d)
+    # shard bounds: contiguous, ordered, cover everything
+    for n in (0, 1, 2, 7, 1000):
+        for w in (1, 2, 4, 8):
+            blocks = [dev.shard_bounds(n, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
