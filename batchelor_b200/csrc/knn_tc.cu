@@ -47,7 +47,7 @@ constexpr int B_BOX_BYTES = BN * 128; // 32 KB
 constexpr int MAX_NBOX = 6;
 constexpr int MAX_MMA_PER_BOX = 6;
 constexpr int MAX_SLOTS = 8;
-constexpr int NUM_THREADS = 192;      // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int NUM_THREADS = 224;      // warp 0: TMA, warps 1 and 6: MMA issuers (even / odd tiles), warps 2..5: epilogue
 constexpr int TMEM_COLS = 512;        // two accumulator stages of BN columns
 constexpr int MAX_K_TENSOR = 56;      // k <= 32*E - 8
 constexpr int MAX_SPLIT = 8;
@@ -374,43 +374,41 @@ __device__ __forceinline__ void compact_rows(unsigned long long* __restrict__ bu
 }
 
 // One 32-column chunk of accumulators (registers v[], lane = query row) against this lane's running threshold.
-// Hot path: one min tree and ONE compare/branch per chunk (a single warp per scheduler has no
-// other latency hiding).  Rare path: the lane appends its hits; appends are overflow-safe (a row that fills up
-// remembers where it stopped, gets compacted and resumes with the tightened threshold).
+// Hot path: one min tree and ONE warp-uniform compare/branch per chunk -- nothing else (a single warp per scheduler
+// has no other latency hiding, and every inlined copy of rare-path code costs instruction cache).  Rare path: the
+// chunk is staged in shared memory (each lane only ever reads back its own slots, so no synchronisation) and the
+// hitting lanes append from a compact runtime loop.  A row whose buffer is full drops the hit and is marked dirty;
+// dirty rows are handed to the exact rescue kernel, so exactness never depends on buffer capacity.
 template <int E>
-__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], const int col0, float& thr, int& cnt, bool& sorted,
-                                             unsigned long long* __restrict__ buf, const int lane) {
-    constexpr int CAP = Cand<E>::CAP;
-    constexpr int SOFT = CAP - 8;
-    float s[32];   // the accumulators ARE the scores (norm and the factor -2 are folded into the MMA)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], const int col0, const float thr, int& cnt, bool& dirty,
+                                           unsigned long long* __restrict__ buf, float4* __restrict__ stg, const int lane) {
     float m[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fminf(fminf(s[4 * j], s[4 * j + 1]), fminf(s[4 * j + 2], s[4 * j + 3]));
+    for (int j = 0; j < 8; ++j)
+        m[j] = fminf(fminf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), fminf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
     const float mm = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
-    int ovf_at = 32;
-    if (mm < thr) {  // rare, per lane
+    if (__any_sync(0xffffffffu, mm < thr)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (s[i] < thr) {
-                if (cnt < CAP) {
-                    buf[cnt * ROWPITCH + lane] = make_key(s[i], col0 + i);
-                    ++cnt;
-                } else if (ovf_at == 32) {
-                    ovf_at = i;
-                }
-            }
-        }
-    }
-    if (__any_sync(0xffffffffu, (cnt > SOFT) | (ovf_at < 32))) {
-        compact_rows<E>(buf, lane, SOFT, thr, cnt, sorted);
-        if (ovf_at < 32) {  // resume the columns this row could not take (room for PEND >= 32 keys is guaranteed now)
+        for (int j = 0; j < 8; ++j)
+            stg[j * 32 + lane] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        // the group minima are still in registers: jump straight to the 4-column groups that contain a hit
+        unsigned gm = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                if (i >= ovf_at && s[i] < thr) {
-                    buf[cnt * ROWPITCH + lane] = make_key(s[i], col0 + i);
-                    ++cnt;
+        for (int j = 0; j < 8; ++j) gm |= (m[j] < thr) ? (1u << j) : 0u;
+        while (gm) {  // per lane; usually zero or one iteration
+            const int j = __ffs(gm) - 1;
+            gm &= gm - 1;
+            const float4 q = stg[j * 32 + lane];
+            const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (qq[i] < thr) {
+                    if (cnt < Cand<E>::CAP) {
+                        buf[cnt * ROWPITCH + lane] = make_key(qq[i], col0 + 4 * j + i);
+                        ++cnt;
+                    } else {
+                        dirty = true;
+                    }
                 }
             }
         }
@@ -443,7 +441,8 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* smA = smem;
     uint8_t* smB = smA + (size_t)nbox * A_BOX_BYTES;
     unsigned long long* lists = reinterpret_cast<unsigned long long*>(smB + (size_t)nslot * B_BOX_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lists + 4 * Cand<E>::WARP_KEYS + 2);
+    float4* stage_all = reinterpret_cast<float4*>(lists + 4 * Cand<E>::WARP_KEYS + 2);   // [4 warps][8][32] float4, 16-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 4 * 8 * 32);
     uint64_t* full = bars;                  // [MAX_SLOTS]
     uint64_t* empty = bars + MAX_SLOTS;     // [MAX_SLOTS]
     uint64_t* afull = bars + 2 * MAX_SLOTS; // [1]
@@ -507,8 +506,11 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
+    } else if (warp == 1 || warp == 6) {
+        // ===================== MMA issuers =====================
+        // tcgen05.mma issue blocks until the tensor pipe accepts the instruction, so every barrier wait / commit of an
+        // issuing thread is dead time for the pipe.  Two issuing warps alternate tiles (warp 1: even tiles = accumulator
+        // stage 0, warp 6: odd tiles = stage 1): while one sits in its waits the other keeps the pipe fed.
         // A single thread has no latency hiding, so the per-tile issue path must be straight-line code: every
         // descriptor of the schedule is precomputed into registers (static indices after unrolling over NBOX x 6).
         // The whole warp runs the loop (warp-uniform values stay in uniform registers); one elected lane issues.
@@ -531,9 +533,8 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint64_t db_base = make_sw128_desc(smem_u32(smB));
             mbar_wait(smem_u32(afull), 0);
             tc_fence_after();
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int tl = 0; tl < my_tiles; ++tl) {
+            const int mma_id = (warp == 1) ? 0 : 1;
+            for (int tl = mma_id; tl < my_tiles; tl += 2) {
                 const int stage = tl & 1;
                 const uint32_t use = (uint32_t)(tl >> 1);
                 B200_TS(tl, 0);
@@ -541,6 +542,9 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 tc_fence_after();
                 B200_TS(tl, 1);
                 const uint32_t tmem_d = tmem_base + (uint32_t)(stage * BN);
+                const int box0 = tl * NBOX;                 // global box counter of this tile's first box
+                int slot = box0 % nslot;
+                uint32_t phase = (uint32_t)((box0 / nslot) & 1);
 #pragma unroll
                 for (int b = 0; b < NBOX; ++b) {
                     mbar_wait(smem_u32(&full[slot]), phase);
@@ -572,10 +576,13 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ===================== epilogue: TMEM -> registers -> threshold filter -> sorted lists =====================
         const int q4 = warp & 3;  // TMEM lane quarter this warp may access
         unsigned long long* mybuf = lists + (size_t)(warp - 2) * Cand<E>::WARP_KEYS;   // this warp's candidate buffers
+        float4* stg = stage_all + (size_t)(warp - 2) * 8 * 32;                       // this warp's staging tile
         int cnt = 0;          // keys currently in this lane's row buffer
         bool sorted = false;  // retained part sorted (true after the first compaction)
+        bool dirty = false;   // this row ever dropped a hit (buffer full) -> certificate must fail -> exact rescue
         float thr = __int_as_float(0x7f800000);
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        constexpr int BOOT_TILES = 6;                       // tiles scanned in bootstrap mode (compaction after every chunk)
         for (int tl = 0; tl < my_tiles; ++tl) {
             const int stage = tl & 1;
             const uint32_t use = (uint32_t)(tl >> 1);
@@ -592,32 +599,64 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (warp == 2) B200_TS(tl, 10);
                 continue;
             }
-            uint32_t va[32], vb[32];
-            tmem_ld32(tbase, va);
-            tmem_ld_wait();
+            if (trace && warp == 2 && tl >= trace_start && tl < trace_start + 64) {
+                const int tot = __reduce_add_sync(0xffffffffu, cnt);
+                if (lane == 0) dbg_ts[(tl - trace_start) * 32 + 24] = tot;
+            }
+            uint32_t v0[32], v1[32], v2[32], v3[32];
+            if (tl < BOOT_TILES) {
+                // Bootstrap: thresholds are still loose (every column of the very first tile is a hit), so rows are
+                // compacted after every chunk; a chunk adds at most 32 = PEND keys, hence no row can overflow here.
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c += 2) {
-                tmem_ld32(tbase + (uint32_t)((c + 1) * 32), vb);   // in flight while chunk c is filtered
-                if (trace && warp == 2 && tl >= trace_start && tl < trace_start + 64 && c == 0) {
-                    const int tot = __reduce_add_sync(0xffffffffu, cnt);
-                    if (lane == 0) dbg_ts[(tl - trace_start) * 32 + 24] = tot;
+                for (int c = 0; c < BN / 32; ++c) {
+                    tmem_ld32(tbase + (uint32_t)(c * 32), v0);
+                    tmem_ld_wait();
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                        if (warp == 2) B200_TS(tl, 10);
+                    }
+                    scan_chunk<E>(v0, colbase + c * 32, thr, cnt, dirty, mybuf, stg, lane);
+                    if (__any_sync(0xffffffffu, cnt > Cand<E>::KEEP)) compact_rows<E>(mybuf, lane, Cand<E>::KEEP, thr, cnt, sorted);
                 }
-                if (dbg_mode != 2) filter_chunk<E>(va, colbase + c * 32, thr, cnt, sorted, mybuf, lane);
-                if (warp == 2) B200_TS(tl, 16 + c);
-                else if (__uint_as_float(va[0]) == 1.2345e-30f && __uint_as_float(va[31]) == 1.2345e-30f) thr = 0.f;
+            } else {
+                // Steady state.  Two 32-column loads are always in flight while two others are scanned: reading freshly
+                // written accumulators out of TMEM runs at ~64 B/cycle/SM, which makes the TMEM read port the limiter of
+                // this kernel (128 KB per tile = ~2k cycles vs ~1.3k cycles of MMA); it must never idle.
+                tmem_ld32(tbase, v0);
+                tmem_ld32(tbase + 32u, v1);
                 tmem_ld_wait();
-                if (c + 2 < BN / 32) {
-                    tmem_ld32(tbase + (uint32_t)((c + 2) * 32), va);
-                } else {  // every column of this stage is now in registers: hand the stage back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
-                    if (warp == 2) B200_TS(tl, 10);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; c += 4) {
+                    tmem_ld32(tbase + (uint32_t)((c + 2) * 32), v2);
+                    tmem_ld32(tbase + (uint32_t)((c + 3) * 32), v3);
+                    if (dbg_mode != 2) {
+                        scan_chunk<E>(v0, colbase + c * 32, thr, cnt, dirty, mybuf, stg, lane);
+                        scan_chunk<E>(v1, colbase + (c + 1) * 32, thr, cnt, dirty, mybuf, stg, lane);
+                    } else if (__uint_as_float(v0[0]) == 1.2345e-30f && __uint_as_float(v1[31]) == 1.2345e-30f) thr = 0.f;
+                    if (warp == 2) B200_TS(tl, 16 + c);
+                    tmem_ld_wait();
+                    if (c + 4 < BN / 32) {
+                        tmem_ld32(tbase + (uint32_t)((c + 4) * 32), v0);
+                        tmem_ld32(tbase + (uint32_t)((c + 5) * 32), v1);
+                    } else {  // every column of this stage is now in registers: hand the stage back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                        if (warp == 2) B200_TS(tl, 10);
+                    }
+                    if (dbg_mode != 2) {
+                        scan_chunk<E>(v2, colbase + (c + 2) * 32, thr, cnt, dirty, mybuf, stg, lane);
+                        scan_chunk<E>(v3, colbase + (c + 3) * 32, thr, cnt, dirty, mybuf, stg, lane);
+                    } else if (__uint_as_float(v2[0]) == 1.2345e-30f && __uint_as_float(v3[31]) == 1.2345e-30f) thr = 0.f;
+                    if (warp == 2) B200_TS(tl, 18 + c);
+                    tmem_ld_wait();
                 }
-                if (dbg_mode != 2) filter_chunk<E>(vb, colbase + (c + 1) * 32, thr, cnt, sorted, mybuf, lane);
-                if (warp == 2) B200_TS(tl, 17 + c);
-                else if (__uint_as_float(vb[0]) == 1.2345e-30f && __uint_as_float(vb[31]) == 1.2345e-30f) thr = 0.f;
-                tmem_ld_wait();
+                // one compaction site per tile (the last tile compacts every row: final sorted lists + thresholds)
+                // (hits per row per tile fall like 48/tl: leave more head-room while they are still frequent)
+                const int limit = (tl == my_tiles - 1) ? -1 : (tl < 32 ? Cand<E>::KEEP + 8 : Cand<E>::KEEP + 16);
+                if (__any_sync(0xffffffffu, cnt > limit)) compact_rows<E>(mybuf, lane, limit, thr, cnt, sorted);
             }
             if (warp == 2) B200_TS(tl, 11);
             if (trace && warp == 2 && tl >= trace_start && tl < trace_start + 64) {
@@ -625,8 +664,9 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (lane == 0) dbg_ts[(tl - trace_start) * 32 + 25] = tot;
             }
         }
-        // final compaction of every row, then write the retained candidates: row r, 32*E entries, coalesced
-        compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);
+        // rows that never saw a steady-state tile still need their final compaction
+        if (my_tiles <= BOOT_TILES) compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);
+        if (dirty) thr = __int_as_float(0xff800000);   // -inf: the re-rank certificate cannot hold -> exact rescue
         const int64_t rowbase = (int64_t)m0 + q4 * 32;
         const int64_t sbase = (int64_t)blockIdx.y * nq;
 #pragma unroll 1
@@ -1028,7 +1068,7 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 }
 
 static size_t candidates_smem_bytes(int nbox, int nslot, int E) {
-    return 1024 /* alignment slack */ + (size_t)nbox * A_BOX_BYTES + (size_t)nslot * B_BOX_BYTES + (size_t)(4 * (32 * E + 32) * ROWPITCH + 2) * 8 +
+    return 1024 /* alignment slack */ + (size_t)nbox * A_BOX_BYTES + (size_t)nslot * B_BOX_BYTES + (size_t)(4 * (32 * E + 32) * ROWPITCH + 2) * 8 + (size_t)4 * 8 * 32 * 16 +
            (2 * MAX_SLOTS + 5) * 8 + 16;
 }
 
@@ -1140,10 +1180,11 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr);
     B200_LAUNCH_CHECK();
 
-    // Thread-block clusters: the CTAs of a cluster work on different query tiles against the SAME stream of reference
-    // boxes; each CTA fetches 1/csize of every box and TMA-multicasts it, which divides the L2->SM traffic (the
-    // limiter of the unclustered kernel: 64 KB per tile per SM = 6 TB/s chip-wide) by csize.
-    int csize = mtiles >= 8 ? 4 : (mtiles >= 2 ? 2 : 1);
+    // Thread-block clusters (optional, B200MNN_CLUSTER=2|4): the CTAs of a cluster work on different query tiles against
+    // the SAME stream of reference boxes; each CTA fetches 1/csize of every box and TMA-multicasts it, dividing the
+    // L2->SM traffic by csize.  Measured on B200 the kernel is NOT L2-bound (TMEM readout and the two-stage accumulator
+    // hand-off are), and lock-stepping the CTAs of a cluster costs 20-25 %, so the default is no cluster.
+    int csize = 1;
     if (const char* ce = getenv("B200MNN_CLUSTER")) {
         const int c = atoi(ce);
         if (c == 1 || c == 2 || c == 4) csize = c;

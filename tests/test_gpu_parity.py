@@ -321,7 +321,8 @@ def test_mnn_correct_matches_oracle():
     # (src/adjust_shift_variance.cpp:145-156) a coin flip on last-bit rounding -- the reference's own tests skip
     # platforms over exactly this (tests/testthat/test-mnn-correct.R:140-141, :396-399).
     for kw in (dict(), dict(var_adj=False), dict(cos_norm_in=False, cos_norm_out=False, sigma=60.0),
-               dict(cos_norm_in=False, cos_norm_out=False, var_adj=False), dict(cos_norm_out=False),
+               dict(cos_norm_in=False, cos_norm_out=False, var_adj=False), dict(cos_norm_out=False, var_adj=False),
+               dict(cos_norm_out=False, sigma=60.0),
                dict(merge_order=[3, 1, 2]), dict(sigma=1.0)):
         got = bb.mnnCorrect(A, B, Cc, k=15, **kw)
         ref = ho.mnn_correct([A, B, Cc], k=15, **kw)
