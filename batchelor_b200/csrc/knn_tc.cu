@@ -325,6 +325,7 @@ __device__ __forceinline__ unsigned long long reverse32(unsigned long long key) 
 template <int E>
 __device__ __forceinline__ void compact_rows(unsigned long long* __restrict__ buf, const int lane, const int limit, float& thr, int& cnt,
                                              bool& sorted) {
+    __syncwarp();
     unsigned todo = __ballot_sync(0xffffffffu, cnt > limit);
     while (todo) {
         const int r = __ffs(todo) - 1;
@@ -374,44 +375,78 @@ __device__ __forceinline__ void compact_rows(unsigned long long* __restrict__ bu
 }
 
 // One 32-column chunk of accumulators (registers v[], lane = query row) against this lane's running threshold.
-// Hot path: one min tree and ONE warp-uniform compare/branch per chunk -- nothing else (a single warp per scheduler
-// has no other latency hiding, and every inlined copy of rare-path code costs instruction cache).  Rare path: the
-// chunk is staged in shared memory (each lane only ever reads back its own slots, so no synchronisation) and the
-// hitting lanes append from a compact runtime loop.  A row whose buffer is full drops the hit and is marked dirty;
-// dirty rows are handed to the exact rescue kernel, so exactness never depends on buffer capacity.
+// Hot path: one min tree (3-input FMNMX3: 16 instructions for 32 scores) and ONE warp-uniform vote/branch per chunk.
+// Rare path (some lane has a score below its threshold): the warp stages the chunk in shared memory (XOR-swizzled so
+// that both the row-wise writes and the column-wise reads below are bank-conflict free), then for every hitting row L
+// the 32 lanes each look at ONE score of that row, vote, and the hitting lanes store their keys side by side at the
+// end of row L's buffer.  No divergent branches and no per-lane search: a chunk with one hit costs ~20 instructions.
+// A row whose buffer is full drops the hit and is marked dirty; dirty rows are handed to the exact rescue kernel, so
+// exactness never depends on buffer capacity.
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float chunk_min(const uint32_t (&v)[32]) {
+#define VF(i) __uint_as_float(v[i])
+    const float t0 = fmin3(VF(0), VF(1), VF(2)), t1 = fmin3(VF(3), VF(4), VF(5)), t2 = fmin3(VF(6), VF(7), VF(8));
+    const float t3 = fmin3(VF(9), VF(10), VF(11)), t4 = fmin3(VF(12), VF(13), VF(14)), t5 = fmin3(VF(15), VF(16), VF(17));
+    const float t6 = fmin3(VF(18), VF(19), VF(20)), t7 = fmin3(VF(21), VF(22), VF(23)), t8 = fmin3(VF(24), VF(25), VF(26));
+    const float t9 = fmin3(VF(27), VF(28), VF(29)), t10 = fminf(VF(30), VF(31));
+    const float u0 = fmin3(t0, t1, t2), u1 = fmin3(t3, t4, t5), u2 = fmin3(t6, t7, t8), u3 = fminf(t9, t10);
+    return fminf(fminf(u0, u1), fminf(u2, u3));
+#undef VF
+}
+// Rare path of a chunk: `hit` = lanes (rows) that have at least one score below their threshold.
+template <int E>
+__device__ __forceinline__ void append_hits(const uint32_t (&v)[32], unsigned hit, const int col0, const float thr, int& cnt, bool& dirty,
+                                            unsigned long long* __restrict__ buf, float4* __restrict__ stg, const int lane, int* stat) {
+#define VF(i) __uint_as_float(v[i])
+    if (stat) { stat[0] += 1; stat[1] += __popc(hit); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) stg[j * 32 + (lane ^ j)] = make_float4(VF(4 * j), VF(4 * j + 1), VF(4 * j + 2), VF(4 * j + 3));
+    __syncwarp();
+    const float* stgf = reinterpret_cast<const float*>(stg);
+    const int g = lane >> 2;
+    do {
+        const int L = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const float thrL = __shfl_sync(0xffffffffu, thr, L);
+        const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+        const float sc = stgf[((g * 32 + (L ^ g)) << 2) + (lane & 3)];   // score of (row L, column col0 + lane)
+        const bool h = sc < thrL;
+        const unsigned m = __ballot_sync(0xffffffffu, h);
+        const int pos = cntL + __popc(m & ((1u << lane) - 1u));
+        if (h && pos < Cand<E>::CAP) buf[pos * ROWPITCH + L] = make_key(sc, col0 + lane);
+        if (stat) stat[2] += __popc(m);
+        if (lane == L) {
+            const int n = cntL + __popc(m);
+            if (n > Cand<E>::CAP) dirty = true;
+            cnt = n > Cand<E>::CAP ? Cand<E>::CAP : n;
+        }
+    } while (hit);
+    __syncwarp();   // staging area is reused by the next chunk; appended keys become visible to the whole warp
+#undef VF
+}
 template <int E>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], const int col0, const float thr, int& cnt, bool& dirty,
-                                           unsigned long long* __restrict__ buf, float4* __restrict__ stg, const int lane) {
-    float m[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        m[j] = fminf(fminf(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), fminf(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-    const float mm = fminf(fminf(fminf(m[0], m[1]), fminf(m[2], m[3])), fminf(fminf(m[4], m[5]), fminf(m[6], m[7])));
-    if (__any_sync(0xffffffffu, mm < thr)) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            stg[j * 32 + lane] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-        // the group minima are still in registers: jump straight to the 4-column groups that contain a hit
-        unsigned gm = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) gm |= (m[j] < thr) ? (1u << j) : 0u;
-        while (gm) {  // per lane; usually zero or one iteration
-            const int j = __ffs(gm) - 1;
-            gm &= gm - 1;
-            const float4 q = stg[j * 32 + lane];
-            const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (qq[i] < thr) {
-                    if (cnt < Cand<E>::CAP) {
-                        buf[cnt * ROWPITCH + lane] = make_key(qq[i], col0 + 4 * j + i);
-                        ++cnt;
-                    } else {
-                        dirty = true;
-                    }
-                }
-            }
-        }
+                                           unsigned long long* __restrict__ buf, float4* __restrict__ stg, const int lane, int* stat = nullptr) {
+    const float mm = chunk_min(v);
+    const unsigned hit = __ballot_sync(0xffffffffu, mm < thr);
+    if (hit) append_hits<E>(v, hit, col0, thr, cnt, dirty, buf, stg, lane, stat);
+}
+// Two chunks behind ONE vote/branch: both min trees interleave (a lone warp per scheduler has nothing else to hide
+// the ALU latency behind) and the quiet path pays one vote instead of two.
+template <int E>
+__device__ __forceinline__ void scan_pair(const uint32_t (&va)[32], const uint32_t (&vb)[32], const int col0, const float thr, int& cnt,
+                                          bool& dirty, unsigned long long* __restrict__ buf, float4* __restrict__ stg, const int lane,
+                                          int* stat = nullptr) {
+    const float ma = chunk_min(va), mb = chunk_min(vb);
+    if (__any_sync(0xffffffffu, fminf(ma, mb) < thr)) {
+        const unsigned ha = __ballot_sync(0xffffffffu, ma < thr);
+        if (ha) append_hits<E>(va, ha, col0, thr, cnt, dirty, buf, stg, lane, stat);
+        const unsigned hb = __ballot_sync(0xffffffffu, mb < thr);
+        if (hb) append_hits<E>(vb, hb, col0 + 32, thr, cnt, dirty, buf, stg, lane, stat);
     }
 }
 
@@ -687,6 +722,343 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     __syncthreads();
     if (csize > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (TS variant): the query operand lives in TMEM
+// ------------------------------------------------------------------------------------------------
+// Same algorithm and epilogue as knn_candidates_kernel, different data flow, motivated by what bounds that kernel:
+//  * SS-mode UMMA fetches A and B from shared memory (96 B/cycle) while TMA writes the next boxes (~47 B/cycle):
+//    the 128 B/cycle shared-memory port is oversubscribed.  Here every epilogue thread writes its own query row into
+//    TMEM once (tcgen05.st, row = lane, two fp16 per 32-bit column) and the MMAs take A from TMEM (TS mode), so the
+//    tensor core reads only B from shared memory.
+//  * With 256-column tiles only two accumulator stages fit in TMEM and the hand-off chain (MMA completion lag ~1.3k
+//    cycles + accumulator read-out ~1.1k + issue) is longer than two tiles of MMA work.  Here tiles are 128 references
+//    wide and THREE accumulator stages (3 x 128 columns) sit next to the A columns (32 per box), and the epilogue
+//    prefetches the next tile's first chunks before it finishes the current tile.
+constexpr int TS_BN = 128;                 // references per tile
+constexpr int TS_STAGES = 3;               // accumulator stages in TMEM
+constexpr int TS_B_BOX_BYTES = TS_BN * 128;  // 16 KB
+constexpr int TS_MAX_NBOX = 4;             // A columns: 32 per box, 3*128 accumulator columns -> at most 4 boxes
+
+__device__ __forceinline__ void umma_f16_ts_impl(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :
+                 : "r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int E, int NBOX>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] query operand rows (global)
+                         const __grid_constant__ CUtensorMap tmB, const MmaSched sched, const int nslot, const int64_t nq,
+                         const int ntiles, const int tiles_per_split,
+                         int32_t* __restrict__ cand_idx,   // [nsplit][nq][32E]
+                         float* __restrict__ cand_score,   // [nsplit][nq][32E] (may be null)
+                         float* __restrict__ thr_out,      // [nsplit][nq]
+                         const int dbg_mode, long long* __restrict__ dbg_ts, const int trace_start) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr int A_COLS = NBOX * 32;                      // TMEM columns holding the query operand
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TS_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+    uint8_t* smB = smem;
+    unsigned long long* lists = reinterpret_cast<unsigned long long*>(smB + (size_t)nslot * TS_B_BOX_BYTES);
+    float4* stage_all = reinterpret_cast<float4*>(lists + 4 * Cand<E>::WARP_KEYS + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 4 * 8 * 32);
+    uint64_t* full = bars;                     // [MAX_SLOTS]
+    uint64_t* empty = bars + MAX_SLOTS;        // [MAX_SLOTS]
+    uint64_t* aready = bars + 2 * MAX_SLOTS;   // [1] query operand is in TMEM (4 epilogue-warp arrivals)
+    uint64_t* tfull = aready + 1;              // [TS_STAGES]
+    uint64_t* tempty = tfull + TS_STAGES;      // [TS_STAGES]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + TS_STAGES);
+
+    const int tile0 = blockIdx.y * tiles_per_split;
+    const int tile1 = min(ntiles, tile0 + tiles_per_split);
+    const int my_tiles = tile1 - tile0;
+    const int m0 = blockIdx.x * BM;
+    const bool trace = dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < nslot; ++i) { mbar_init(smem_u32(&full[i]), 1); mbar_init(smem_u32(&empty[i]), 1); }
+        mbar_init(smem_u32(aready), 4);
+        for (int i = 0; i < TS_STAGES; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_base = tmem_base + (uint32_t)A_COLS;   // accumulator stage s at columns A_COLS + s*TS_BN
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int t = tile0; t < tile1; ++t) {
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b) {
+                    mbar_wait(smem_u32(&empty[slot]), phase ^ 1);
+                    if (dbg_mode == 3) {
+                        mbar_arrive(smem_u32(&full[slot]));
+                    } else {
+                        mbar_arrive_expect_tx(smem_u32(&full[slot]), (uint32_t)TS_B_BOX_BYTES);
+                        tma_load_2d(smem_u32(smB + (size_t)slot * TS_B_BOX_BYTES), &tmB, smem_u32(&full[slot]), b * KBOX, t * TS_BN);
+                    }
+                    if (++slot == nslot) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 6) {
+        // ===================== MMA issuers (even / odd tiles) =====================
+        uint32_t aT[NBOX][MAX_MMA_PER_BOX];   // TMEM address of the A slice of every scheduled MMA
+        uint32_t oB[NBOX][MAX_MMA_PER_BOX];
+        int nm[NBOX];
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) {
+            nm[b] = sched.nmma[b];
+#pragma unroll
+            for (int m = 0; m < MAX_MMA_PER_BOX; ++m) {
+                aT[b][m] = tmem_base + (uint32_t)sched.a_slice[b][m] * 8u;   // 16 fp16 of K = 8 columns per slice
+                oB[b][m] = (uint32_t)sched.b_sub[b][m] * 2u;
+            }
+        }
+        const uint64_t db_base = make_sw128_desc(smem_u32(smB));
+        mbar_wait(smem_u32(aready), 0);
+        tc_fence_after();
+        const int mma_id = (warp == 1) ? 0 : 1;
+#define TS_STAMP(k)                                                                                                   \
+    do {                                                                                                              \
+        if (trace && lane == 0 && tl >= trace_start && tl < trace_start + 64) dbg_ts[(tl - trace_start) * 32 + (k)] = clock64(); \
+    } while (0)
+        for (int tl = mma_id; tl < my_tiles; tl += 2) {
+            const int stage = tl % TS_STAGES;
+            const uint32_t use = (uint32_t)(tl / TS_STAGES);
+            TS_STAMP(0);
+            mbar_wait(smem_u32(&tempty[stage]), (use & 1) ^ 1);
+            tc_fence_after();
+            TS_STAMP(1);
+            const uint32_t tmem_d = acc_base + (uint32_t)(stage * TS_BN);
+            const int box0 = tl * NBOX;
+            int slot = box0 % nslot;
+            uint32_t phase = (uint32_t)((box0 / nslot) & 1);
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {
+                mbar_wait(smem_u32(&full[slot]), phase);
+                tc_fence_after();
+                TS_STAMP(2 + 2 * (b < 2 ? b : 1));
+                const uint64_t db0 = db_base + (uint64_t)((uint32_t)slot * (uint32_t)(TS_B_BOX_BYTES >> 4));
+                if (elect_one()) {
+                    if (dbg_mode != 4) {
+#pragma unroll
+                        for (int m = 0; m < MAX_MMA_PER_BOX; ++m)
+                            if (m < nm[b]) umma_f16_ts_impl(tmem_d, aT[b][m], db0 + oB[b][m], idesc, (b == 0 && m == 0) ? 0u : 1u);
+                    }
+                    umma_commit(smem_u32(&empty[slot]));
+                    if (b == NBOX - 1) umma_commit(smem_u32(&tfull[stage]));
+                }
+                __syncwarp();
+                TS_STAMP(3 + 2 * (b < 2 ? b : 1));
+                if (++slot == nslot) { slot = 0; phase ^= 1; }
+            }
+        }
+#undef TS_STAMP
+    } else {
+        // ===================== epilogue =====================
+        const int q4 = warp & 3;
+        const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+        // (1) this thread's query row -> TMEM (A operand of every MMA of this CTA)
+        {
+            const uint4* arow = reinterpret_cast<const uint4*>(opA + ((size_t)m0 + q4 * 32 + lane) * (NBOX * KBOX));
+#pragma unroll
+            for (int sl = 0; sl < NBOX * 4; ++sl) {
+                const uint4 lo = __ldg(arow + 2 * sl), hi = __ldg(arow + 2 * sl + 1);
+                tmem_st8(tmem_base + lane_sel + (uint32_t)(sl * 8), lo, hi);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(aready));
+        }
+        unsigned long long* mybuf = lists + (size_t)(warp - 2) * Cand<E>::WARP_KEYS;
+        float4* stg = stage_all + (size_t)(warp - 2) * 8 * 32;
+        int cnt = 0;
+        bool sorted = false, dirty = false;
+        float thr = __int_as_float(0x7f800000);
+        const uint32_t lane_acc = acc_base + lane_sel;
+        constexpr int BOOT_TILES = 12;   // 12 x 128 columns scanned with a compaction after every chunk
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        long long acc_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // measurement aid (trace only)
+        int stat[3] = {0, 0, 0};
+        long long qt[2] = {0, 0};
+        int tl = 0;
+        // ---- bootstrap tiles (non-pipelined) ----
+        for (; tl < my_tiles && tl < BOOT_TILES; ++tl) {
+            const int stage = tl % TS_STAGES;
+            mbar_wait(smem_u32(&tfull[stage]), (uint32_t)((tl / TS_STAGES) & 1));
+            tc_fence_after();
+            const int colbase = (tile0 + tl) * TS_BN;
+            const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
+#pragma unroll 1
+            for (int c = 0; c < TS_BN / 32; ++c) {
+                tmem_ld32(tbase + (uint32_t)(c * 32), v0);
+                tmem_ld_wait();
+                if (c == TS_BN / 32 - 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                }
+                if (dbg_mode == 0) {
+                    scan_chunk<E>(v0, colbase + c * 32, thr, cnt, dirty, mybuf, stg, lane);
+                    if (__any_sync(0xffffffffu, cnt > Cand<E>::KEEP)) compact_rows<E>(mybuf, lane, Cand<E>::KEEP, thr, cnt, sorted);
+                }
+            }
+        }
+        // ---- steady state: the first two chunks of the next tile are requested before this tile's last two are scanned ----
+        if (tl < my_tiles) {
+            const int stage = tl % TS_STAGES;
+            mbar_wait(smem_u32(&tfull[stage]), (uint32_t)((tl / TS_STAGES) & 1));
+            tc_fence_after();
+            const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
+            tmem_ld32(tbase, v0);
+            tmem_ld32(tbase + 32u, v1);
+        }
+        for (; tl < my_tiles; ++tl) {
+            const int stage = tl % TS_STAGES;
+            const int colbase = (tile0 + tl) * TS_BN;
+            const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
+            if (trace && warp == 2 && lane == 0 && tl >= trace_start && tl < trace_start + 64) dbg_ts[(tl - trace_start) * 32 + 9] = clock64();
+            if (dbg_mode == 1) {  // measurement aid: MMA pipeline alone, stages are recycled without being read
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                if (tl + 1 < my_tiles) {
+                    const int nstage = (tl + 1) % TS_STAGES;
+                    mbar_wait(smem_u32(&tfull[nstage]), (uint32_t)(((tl + 1) / TS_STAGES) & 1));
+                    tc_fence_after();
+                }
+                continue;
+            }
+            if (dbg_mode == 5) {  // measurement aid: no TMEM load in flight while a chunk is scanned
+                long long d0 = clock64();
+                tmem_ld_wait();
+                long long d1 = clock64();
+                scan_pair<E>(v0, v1, colbase, thr, cnt, dirty, mybuf, stg, lane, trace ? stat : nullptr);
+                long long d2 = clock64();
+                tmem_ld32(tbase + 64u, v0);
+                tmem_ld32(tbase + 96u, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                long long d3 = clock64();
+                scan_pair<E>(v0, v1, colbase + 64, thr, cnt, dirty, mybuf, stg, lane, trace ? stat : nullptr);
+                long long d4 = clock64();
+                const int limit5 = (tl == my_tiles - 1) ? -1 : (tl < 64 ? Cand<E>::KEEP + 8 : Cand<E>::KEEP + 16);
+                if (__any_sync(0xffffffffu, cnt > limit5)) compact_rows<E>(mybuf, lane, limit5, thr, cnt, sorted);
+                long long d5 = clock64();
+                if (tl + 1 < my_tiles) {
+                    const int nstage = (tl + 1) % TS_STAGES;
+                    mbar_wait(smem_u32(&tfull[nstage]), (uint32_t)(((tl + 1) / TS_STAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t nbase = lane_acc + (uint32_t)(nstage * TS_BN);
+                    tmem_ld32(nbase, v0);
+                    tmem_ld32(nbase + 32u, v1);
+                }
+                long long d6 = clock64();
+                acc_t[0] += d1 - d0; acc_t[1] += d2 - d1; acc_t[2] += d3 - d2; acc_t[3] += d6 - d5; acc_t[4] += d4 - d3; acc_t[5] += d5 - d4; acc_t[7] += 1;
+                continue;
+            }
+            long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0;
+            if (trace) c0 = clock64();
+            tmem_ld_wait();                                   // chunks 0,1 of this tile
+            tmem_ld32(tbase + 64u, v2);
+            tmem_ld32(tbase + 96u, v3);
+            const int hc0 = stat[0];
+            if (trace) c1 = clock64();
+            if (dbg_mode == 0) {
+                scan_pair<E>(v0, v1, colbase, thr, cnt, dirty, mybuf, stg, lane, trace ? stat : nullptr);
+            } else if (__uint_as_float(v0[0]) == 1.2345e-30f && __uint_as_float(v1[31]) == 1.2345e-30f) thr = 0.f;
+            if (trace) c2 = clock64();
+            tmem_ld_wait();                                   // chunks 2,3: the whole stage is in registers now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+            if (trace && warp == 2 && lane == 0 && tl >= trace_start && tl < trace_start + 64) dbg_ts[(tl - trace_start) * 32 + 10] = clock64();
+            if (trace) c3 = clock64();
+            if (tl + 1 < my_tiles) {
+                const int nstage = (tl + 1) % TS_STAGES;
+                mbar_wait(smem_u32(&tfull[nstage]), (uint32_t)(((tl + 1) / TS_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t nbase = lane_acc + (uint32_t)(nstage * TS_BN);
+                tmem_ld32(nbase, v0);
+                tmem_ld32(nbase + 32u, v1);
+            }
+            if (trace) c4 = clock64();
+            if (dbg_mode == 0) {
+                scan_pair<E>(v2, v3, colbase + 64, thr, cnt, dirty, mybuf, stg, lane, trace ? stat : nullptr);
+            } else if (__uint_as_float(v2[0]) == 1.2345e-30f && __uint_as_float(v3[31]) == 1.2345e-30f) thr = 0.f;
+            if (trace) c5 = clock64();
+            const int limit = (tl == my_tiles - 1) ? -1 : (tl < 64 ? Cand<E>::KEEP + 8 : Cand<E>::KEEP + 16);
+            const bool need = __any_sync(0xffffffffu, cnt > limit);
+            if (need) compact_rows<E>(mybuf, lane, limit, thr, cnt, sorted);
+            if (trace) {
+                c6 = clock64();
+                acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; acc_t[2] += c3 - c2; acc_t[3] += c4 - c3; acc_t[4] += c5 - c4; acc_t[5] += c6 - c5;
+                acc_t[6] += need ? 1 : 0; acc_t[7] += 1;
+                if (stat[0] == hc0) { qt[0] += (c2 - c1) + (c5 - c4); qt[1] += 1; }
+            }
+            if (trace && warp == 2 && lane == 0 && tl >= trace_start && tl < trace_start + 64) dbg_ts[(tl - trace_start) * 32 + 11] = clock64();
+        }
+        if (trace && lane == 0)
+            for (int i = 0; i < 8; ++i) dbg_ts[64 * 32 + (warp - 2) * 8 + i] = acc_t[i];
+        if (trace && lane == 0)
+            for (int i = 0; i < 3; ++i) dbg_ts[64 * 32 + 32 + (warp - 2) * 4 + i] = stat[i];
+        if (trace && lane == 0) { dbg_ts[64 * 32 + 48 + (warp - 2) * 2] = qt[0]; dbg_ts[64 * 32 + 48 + (warp - 2) * 2 + 1] = qt[1]; }
+        if (my_tiles <= BOOT_TILES || dbg_mode != 0) compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);
+        if (dirty) thr = __int_as_float(0xff800000);
+        const int64_t rowbase = (int64_t)m0 + q4 * 32;
+        const int64_t sbase = (int64_t)blockIdx.y * nq;
+#pragma unroll 1
+        for (int r = 0; r < 32; ++r) {
+            const int64_t row = rowbase + r;
+            if (row < nq) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const unsigned long long key = mybuf[(lane + 32 * e) * ROWPITCH + r];
+                    const int64_t o = (sbase + row) * (32 * E) + lane + 32 * e;
+                    cand_idx[o] = (int32_t)(uint32_t)key;
+                    if (cand_score) cand_score[o] = key_score(key);
+                }
+            }
+        }
+        if (rowbase + lane < nq) thr_out[sbase + rowbase + lane] = thr;
+        tc_fence_before();
+    }
+    __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -1145,8 +1517,13 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     const int KS = L.nbox * KBOX;
     const int E = (k <= 24) ? 1 : 2;
     const int per = 32 * E;
-    const int64_t n_pad = round_up(n, BN), nq_pad = round_up(nq, BM);
-    const int ntiles = (int)(n_pad / BN);
+    // TS variant (query operand in TMEM, 128-reference tiles, three accumulator stages) unless the operand is too wide
+    // for the TMEM columns left next to the accumulators, or B200MNN_KERNEL=ss asks for the shared-memory variant.
+    const char* kenv = getenv("B200MNN_KERNEL");
+    const bool use_ts = L.nbox <= TS_MAX_NBOX && !(kenv && strcmp(kenv, "ss") == 0);
+    const int bn = use_ts ? TS_BN : BN;
+    const int64_t n_pad = round_up(n, bn), nq_pad = round_up(nq, BM);
+    const int ntiles = (int)(n_pad / bn);
     const int mtiles = (int)(nq_pad / BM);
     int nsplit = 1;
     if (mtiles < 2 * sm_count()) nsplit = (int)std::min<int64_t>(std::min<int64_t>(MAX_SPLIT, ntiles), ceil_div(2 * sm_count(), mtiles));
@@ -1191,14 +1568,25 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     }
     CUtensorMap tmA, tmB;
     B200_TRY(make_operand_map(&tmA, opA, nq_pad, KS, BM));
-    B200_TRY(make_operand_map(&tmB, opB, n_pad, KS, BN / csize));
+    if (use_ts) csize = 1;
+    B200_TRY(make_operand_map(&tmB, opB, n_pad, KS, bn / csize));
 
     int dev = 0, max_smem = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     int nslot = MAX_SLOTS;
-    while (nslot > 3 && candidates_smem_bytes(L.nbox, nslot, E) > (size_t)max_smem) --nslot;
-    const size_t smem = candidates_smem_bytes(L.nbox, nslot, E);
+    size_t smem = 0;
+    if (use_ts) {
+        auto ts_bytes = [&](int ns) {
+            return (size_t)1024 + (size_t)ns * TS_B_BOX_BYTES + (size_t)(4 * (32 * E + 32) * ROWPITCH + 2) * 8 + (size_t)4 * 8 * 32 * 16 +
+                   (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
+        };
+        while (nslot > 2 * L.nbox && ts_bytes(nslot) > (size_t)max_smem) --nslot;
+        smem = ts_bytes(nslot);
+    } else {
+        while (nslot > 3 && candidates_smem_bytes(L.nbox, nslot, E) > (size_t)max_smem) --nslot;
+        smem = candidates_smem_bytes(L.nbox, nslot, E);
+    }
     if (smem > (size_t)max_smem) return fail(B200MNN_ECUDA, "device does not offer enough shared memory per block for the kNN kernel");
     const char* dbg_env = getenv("B200MNN_DEBUG_MODE");   // measurement aid only (results are wrong when non-zero)
     const int dbg_mode = dbg_env ? atoi(dbg_env) : 0;
@@ -1214,9 +1602,9 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     long long* dbg_ts = nullptr;
     const int trace_start = getenv("B200MNN_TRACE") ? atoi(getenv("B200MNN_TRACE")) : 0;
     if (getenv("B200MNN_TRACE")) {  // measurement aid: per-tile clock64 trace of CTA (0,0), printed after the launch
-        dbg_ts = ws.get<long long>(64 * 32);
+        dbg_ts = ws.get<long long>(64 * 32 + 64);
         if (!dbg_ts) return B200MNN_ENOMEM;
-        B200_CUDA(cudaMemsetAsync(dbg_ts, 0, sizeof(long long) * 64 * 32, stream));
+        B200_CUDA(cudaMemsetAsync(dbg_ts, 0, sizeof(long long) * (64 * 32 + 64), stream));
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)round_up(mtiles, csize), (unsigned)nsplit, 1);   // padding CTAs see only zero-filled query rows
@@ -1242,6 +1630,26 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         if (E == 1) B200_LAUNCH_CAND(1, NB); \
         else B200_LAUNCH_CAND(2, NB);        \
     } while (0)
+#define B200_LAUNCH_TS(EE, NB)                                                                                                   \
+    do {                                                                                                                          \
+        B200_CUDA(cudaFuncSetAttribute(knn_candidates_ts_kernel<EE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_ts_kernel<EE, NB>, opA_c, tmB, sched, nslot, nq_c, ntiles,               \
+                                     tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start));                 \
+    } while (0)
+#define B200_LAUNCH_TS_E(NB)               \
+    do {                                   \
+        if (E == 1) B200_LAUNCH_TS(1, NB); \
+        else B200_LAUNCH_TS(2, NB);        \
+    } while (0)
+    const __half* opA_c = opA;
+    if (use_ts) {
+        switch (L.nbox) {
+            case 1: B200_LAUNCH_TS_E(1); break;
+            case 2: B200_LAUNCH_TS_E(2); break;
+            case 3: B200_LAUNCH_TS_E(3); break;
+            default: B200_LAUNCH_TS_E(4); break;
+        }
+    } else
     switch (L.nbox) {
         case 1: B200_LAUNCH_CAND_E(1); break;
         case 2: B200_LAUNCH_CAND_E(2); break;
@@ -1252,9 +1660,11 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     }
 #undef B200_LAUNCH_CAND_E
 #undef B200_LAUNCH_CAND
+#undef B200_LAUNCH_TS_E
+#undef B200_LAUNCH_TS
     B200_LAUNCH_CHECK();
     if (dbg_ts) {
-        static long long h[64 * 32];
+        static long long h[64 * 32 + 64];
         B200_CUDA(cudaMemcpyAsync(h, dbg_ts, sizeof(h), cudaMemcpyDeviceToHost, stream));
         B200_CUDA(cudaStreamSynchronize(stream));
         const long long t00 = h[0];
@@ -1265,6 +1675,15 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
             fprintf(stderr, "  chunks:");
             for (int k2 = 16; k2 < 24; ++k2) fprintf(stderr, " %5lld", h[t * 32 + k2] ? h[t * 32 + k2] - h[t * 32 + 9] : -1LL);
             fprintf(stderr, " cnt0=%lld cnt1=%lld\n", h[t * 32 + 24], h[t * 32 + 25]);
+        }
+        for (int w = 0; w < 4; ++w) {
+            const long long* a = h + 64 * 32 + w * 8;
+            const double nt = a[7] ? (double)a[7] : 1.0;
+            fprintf(stderr, "epilogue warp %d, cycles/tile: ldwait0 %.0f scan01 %.0f ldwait1 %.0f tfull %.0f scan23 %.0f compact %.0f (compactions %lld of %lld tiles)\n", w,
+                    a[0] / nt, a[1] / nt, a[2] / nt, a[3] / nt, a[4] / nt, a[5] / nt, a[6], a[7]);
+            const long long* st = h + 64 * 32 + 32 + w * 4;
+            const long long* q = h + 64 * 32 + 48 + w * 2;
+            fprintf(stderr, "   hit chunks %lld, hit rows %lld, appended keys %lld; quiet tiles %lld with %.0f scan cycles each\n", st[0], st[1], st[2], q[1], q[1] ? (double)q[0] / q[1] : 0.0);
         }
     }
     if (ev0) {
