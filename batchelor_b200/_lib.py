@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libb200mnn.so")
+# B200MNN_LIB: load a differently built copy of the same library (kernel A/B measurements on one box)
+LIB_PATH = os.environ.get("B200MNN_LIB") or os.path.join(HERE, "lib", "libb200mnn.so")
 
 i64 = C.c_int64
 i32p = C.POINTER(C.c_int32)

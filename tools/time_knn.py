@@ -10,7 +10,14 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 nq = int(sys.argv[4]) if len(sys.argv) > 4 else n
 X, Q = synth.pc_batches(2, [n, nq], d=50)
 Xd, Qd = torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda()
+import ctypes as C
+from batchelor_b200 import _lib
 for rep in range(reps):
+    _lib.call("b200mnn_profile_enable", 1)
     torch.cuda.synchronize(); t0 = time.time()
     idx, dist = dev.query_knn(Xd, Qd, k)
-    torch.cuda.synchronize(); print(f"{n} refs x {nq} queries k={k}: {time.time() - t0:.4f} s")
+    torch.cuda.synchronize(); dt = time.time() - t0
+    kms, kl, kf = C.c_double(0), C.c_int64(0), C.c_double(0)
+    _lib.call("b200mnn_profile_collect", C.byref(kms), C.byref(kl), C.byref(kf))
+    _lib.call("b200mnn_profile_enable", 0)
+    print(f"{n} refs x {nq} queries k={k}: {dt:.4f} s (candidates kernel {kms.value / 1e3:.4f} s)")
