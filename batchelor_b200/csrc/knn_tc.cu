@@ -45,7 +45,7 @@ constexpr int SLICE = 16;             // K of one tcgen05.mma kind::f16
 constexpr int A_BOX_BYTES = BM * 128; // 16 KB
 constexpr int B_BOX_BYTES = BN * 128; // 32 KB
 constexpr int MAX_NBOX = 6;
-constexpr int MAX_MMA_PER_BOX = 6;
+constexpr int MAX_MMA_PER_BOX = 8;   // a box holds 4 slices; a hi slice of B feeds two MMAs (ah.bh, al.bh)
 constexpr int MAX_SLOTS = 8;
 constexpr int NUM_THREADS = 224;      // warp 0: TMA, warps 1 and 6: MMA issuers (even / odd tiles), warps 2..5: epilogue
 constexpr int TMEM_COLS = 512;        // two accumulator stages of BN columns
@@ -61,16 +61,21 @@ struct MmaSched {
 
 // Stored K layout of one operand row (both operands).  With S the common power-of-two scale:
 //   query row     a = -2*S*q  split as a = ah + al (+O(2^-22));     reference row  b = S*x = bh + bl (+O(2^-22))
-// For every full group g of 16 dims the "hi" slice sits at 2g and the "lo" slice at 2g+1 (three MMAs: ah.bh, al.bh,
-// ah.bl).  If r = d % 16 dims remain and 3r <= 16 they are packed into one remainder slice
+// PRIMARY slices come first: the "hi" slice of every full group g of 16 dims (slice g), then -- if r = d % 16 dims
+// remain and 3r <= 16 -- one remainder slice
 //   query row : [ah(r) | ah(r) | al(r) | ...]      reference row : [bh(r) | bl(r) | bh(r) | ...]
 // whose single MMA yields ah.bh + ah.bl + al.bh for those dims (if 3r > 16 the remainder is zero-padded into one more
 // full group).  Three more columns fold the reference norm into the same accumulation:
 //   query row : [2^15, 2^4, 2^-7]                   reference row : N = S^2 ||x||^2 split as 2^15 n1 + 2^4 n2 + 2^-7 n3
 // so the accumulator IS the score S^2 (||x||^2 - 2 q.x): the epilogue needs neither loads nor FMAs.  The norm
 // columns share the remainder slice when 3r + 3 <= 16, else they get a slice (and one MMA) of their own.
+// The "lo" slices of the full groups follow the primary slices (slice nprim + g).  Two schedules use this layout:
+//   precise : per group ah.bh, al.bh, ah.bl (3 MMAs) + remainder/norm        -> error ~2^-22 relative
+//   fast    : per group ah.bh only (1 MMA) + remainder/norm, reading only the boxes that hold primary slices
+//             -> error <= ~2^-9 |q| |x|, 2.5x fewer MMAs and half the operand traffic for d = 50
 struct KLayout {
     int d, groups, rem, nslices, nbox;
+    int nprim, nbox_fast;       // primary slices (hi, remainder, norm) and the boxes that hold them
     int norm_slice, norm_col;   // stored slice and first column (0..13) of the three norm columns
     int rem_slice;              // stored slice of the packed remainder dims (-1 if none)
 };
@@ -81,37 +86,39 @@ static KLayout make_layout(int d) {
     L.groups = d / SLICE;
     L.rem = d % SLICE;
     if (L.rem * 3 > SLICE) { L.groups += 1; L.rem = 0; }
-    int ns = 2 * L.groups;
+    int ns = L.groups;
     L.rem_slice = -1;
     if (L.rem) L.rem_slice = ns++;
     if (L.rem && 3 * L.rem + 3 <= SLICE) { L.norm_slice = L.rem_slice; L.norm_col = 3 * L.rem; }
     else { L.norm_slice = ns++; L.norm_col = 0; }
-    L.nslices = ns;
+    L.nprim = ns;
+    L.nslices = L.nprim + L.groups;
     L.nbox = (L.nslices + 3) / 4;
+    L.nbox_fast = (L.nprim + 3) / 4;
     return L;
 }
 
-static MmaSched make_sched(const KLayout& L) {
+static MmaSched make_sched(const KLayout& L, bool fast) {
     MmaSched s;
     memset(&s, 0, sizeof(s));
-    s.nbox = L.nbox;
+    s.nbox = fast ? L.nbox_fast : L.nbox;
+    auto add = [&](int a_slice, int b_slice) {
+        const int box = b_slice / 4;
+        int& m = s.nmma[box];
+        s.a_slice[box][m] = (unsigned char)a_slice;
+        s.b_sub[box][m] = (unsigned char)(b_slice % 4);
+        ++m;
+    };
     for (int g = 0; g < L.groups; ++g) {
-        const int sh = 2 * g, sl = 2 * g + 1, box = sh / 4;
-        int& m = s.nmma[box];
-        s.a_slice[box][m] = (unsigned char)sh; s.b_sub[box][m] = (unsigned char)(sh % 4); ++m;  // ah.bh
-        s.a_slice[box][m] = (unsigned char)sl; s.b_sub[box][m] = (unsigned char)(sh % 4); ++m;  // al.bh
-        s.a_slice[box][m] = (unsigned char)sh; s.b_sub[box][m] = (unsigned char)(sl % 4); ++m;  // ah.bl
+        const int sh = g, sl = L.nprim + g;
+        add(sh, sh);                       // ah.bh
+        if (!fast) {
+            add(sl, sh);                   // al.bh
+            add(sh, sl);                   // ah.bl
+        }
     }
-    if (L.rem_slice >= 0) {
-        const int sr = L.rem_slice, box = sr / 4;
-        int& m = s.nmma[box];
-        s.a_slice[box][m] = (unsigned char)sr; s.b_sub[box][m] = (unsigned char)(sr % 4); ++m;
-    }
-    if (L.norm_slice != L.rem_slice) {
-        const int sn = L.norm_slice, box = sn / 4;
-        int& m = s.nmma[box];
-        s.a_slice[box][m] = (unsigned char)sn; s.b_sub[box][m] = (unsigned char)(sn % 4); ++m;
-    }
+    if (L.rem_slice >= 0) add(L.rem_slice, L.rem_slice);
+    if (L.norm_slice != L.rem_slice) add(L.norm_slice, L.norm_slice);
     return s;
 }
 
@@ -327,10 +334,13 @@ __device__ __forceinline__ float key_score(unsigned long long k) {
 __device__ __forceinline__ unsigned long long umin64(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
 __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a < b ? b : a; }
 
-// The two networks below are deliberately NOT unrolled: merge code is cold, and cold code is paid for in instruction
-// fetches (6 KB L0 per scheduler, 32 KB L1.5 per SM; measured: an unrolled merge cost ~5k cycles per row, mostly
-// waiting for its own instructions).  One shuffle stage per loop iteration keeps a whole merge in a few cache lines.
-// bitonic sort of one key per lane, ascending by lane
+// Bitonic networks over NR independent key sets at once (one key of every set per lane).  Measured on B200: one
+// network stage costs ~61 cycles for one row (SHFL latency + 64-bit compare/select) but ~175 cycles for four
+// interleaved rows -- the integer compare/select work runs on the half-rate ALU pipe and dominates, so batching rows
+// buys little and hurts when a call has fewer rows than the batch; NR = 1 is the default.
+#ifndef B200_MERGE_ROWS
+#define B200_MERGE_ROWS 1
+#endif
 #ifndef B200_SORT_ROLLED
 #define B200_SORT_ROLLED 0
 #endif
@@ -339,79 +349,122 @@ __device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsig
 #else
 #define B200_SORT_UNROLL _Pragma("unroll")
 #endif
-__device__ __forceinline__ unsigned long long sort32(unsigned long long key, const int lane) {
+constexpr int MERGE_ROWS = B200_MERGE_ROWS;
+// bitonic sort of one key per lane, ascending by lane
+template <int NR>
+__device__ __forceinline__ void sort32n(unsigned long long (&key)[NR], const int lane) {
     B200_SORT_UNROLL
     for (int k = 2; k <= 32; k <<= 1) {
         B200_SORT_UNROLL
         for (int j = k >> 1; j > 0; j >>= 1) {
-            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
             const bool up = (lane & k) == 0;                     // ascending block? (k == 32: always)
             const bool low = (lane & j) == 0;                    // lower partner of the pair?
-            key = (up == low) ? umin64(key, other) : umax64(key, other);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[i], j);
+                key[i] = ((key[i] < other) == (up == low)) ? key[i] : other;   // one 64-bit compare, one select
+            }
         }
     }
-    return key;
 }
 // bitonic sequence (one key per lane) -> ascending
-__device__ __forceinline__ unsigned long long clean32(unsigned long long key, const int lane) {
+template <int NR>
+__device__ __forceinline__ void clean32n(unsigned long long (&key)[NR], const int lane) {
     B200_SORT_UNROLL
     for (int j = 16; j > 0; j >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j);
-        key = ((lane & j) == 0) ? umin64(key, other) : umax64(key, other);
+        const bool low = (lane & j) == 0;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[i], j);
+            key[i] = ((key[i] < other) == low) ? key[i] : other;
+        }
     }
-    return key;
 }
 __device__ __forceinline__ unsigned long long reverse32(unsigned long long key) { return __shfl_xor_sync(0xffffffffu, key, 31); }
+
+// Merges, for NR rows at once, the pending keys p[] (unsorted, one per lane, EMPTY_KEY where none) into the kept keys
+// a0[] (E == 1) or a0[] <= a1[] (E == 2); sort_kept: the kept keys are not sorted yet (first merge of a row).
+template <int E, int NR>
+__device__ __forceinline__ void merge_keys(unsigned long long (&a0)[NR], unsigned long long (&a1)[NR], unsigned long long (&p)[NR],
+                                           const bool sort_kept, const int lane) {
+    if (sort_kept) {   // warp-uniform
+        sort32n<NR>(a0, lane);
+        if (E == 2) {
+            sort32n<NR>(a1, lane);
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const unsigned long long ra = reverse32(a1[i]);
+                const unsigned long long lo = umin64(a0[i], ra), hi = umax64(a0[i], ra);
+                a0[i] = lo;
+                a1[i] = hi;
+            }
+            clean32n<NR>(a0, lane);
+            clean32n<NR>(a1, lane);                                 // now a0 <= a1 elementwise, both sorted
+        }
+    }
+    sort32n<NR>(p, lane);
+    if (E == 1) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) a0[i] = umin64(a0[i], reverse32(p[i]));
+        clean32n<NR>(a0, lane);                                     // the 32 smallest of both, sorted
+    } else {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) p[i] = umin64(a1[i], reverse32(p[i]));
+        clean32n<NR>(p, lane);                                      // 32 smallest of (a1 u p); the rest is dropped
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const unsigned long long rl = reverse32(p[i]);
+            const unsigned long long lo = umin64(a0[i], rl), hi = umax64(a0[i], rl);
+            a0[i] = lo;
+            a1[i] = hi;
+        }
+        clean32n<NR>(a0, lane);
+        clean32n<NR>(a1, lane);
+    }
+}
 
 // Compacts every row whose lane has cnt > limit.  buf: this warp's CAP x ROWPITCH keys.
 // (Inlined on purpose: as a call it forced thr/cnt and the live TMEM registers of the caller into local memory.)
 template <int E>
 __device__ __forceinline__ void compact_rows(unsigned long long* __restrict__ buf, const int lane, const int limit, float& thr, int& cnt,
                                              bool& sorted) {
+    constexpr int NR = MERGE_ROWS;
     __syncwarp();
     unsigned todo = __ballot_sync(0xffffffffu, cnt > limit);
+    const bool sort_kept = __any_sync(0xffffffffu, cnt > limit && !sorted);   // sorting sorted keys again is harmless
     while (todo) {
-        const int r = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int c = __shfl_sync(0xffffffffu, cnt, r);
-        const bool was_sorted = __shfl_sync(0xffffffffu, (int)sorted, r) != 0;
-        unsigned long long a0 = (lane < c) ? buf[lane * ROWPITCH + r] : EMPTY_KEY;
-        unsigned long long lastkey;
-        if (E == 1) {
-            unsigned long long p = (lane + 32 < c) ? buf[(lane + 32) * ROWPITCH + r] : EMPTY_KEY;
-            if (!was_sorted) a0 = sort32(a0, lane);
-            p = sort32(p, lane);
-            a0 = clean32(umin64(a0, reverse32(p)), lane);          // the 32 smallest of both, sorted
-            buf[lane * ROWPITCH + r] = a0;
-            lastkey = a0;
-        } else {
-            unsigned long long a1 = (lane + 32 < c) ? buf[(lane + 32) * ROWPITCH + r] : EMPTY_KEY;
-            unsigned long long p = (lane + 64 < c) ? buf[(lane + 64) * ROWPITCH + r] : EMPTY_KEY;
-            if (!was_sorted) {
-                a0 = sort32(a0, lane);
-                a1 = sort32(a1, lane);
-                const unsigned long long ra = reverse32(a1);
-                const unsigned long long lo = umin64(a0, ra), hi = umax64(a0, ra);
-                a0 = clean32(lo, lane);
-                a1 = clean32(hi, lane);                             // now a0 <= a1 elementwise, both sorted
+        int r[NR], c[NR];
+        unsigned long long a0[NR], a1[NR], p[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            r[i] = todo ? __ffs(todo) - 1 : -1;                    // -1: batch slot unused (computed on row r[0], not stored)
+            todo &= todo - 1;
+            const int rr = r[i] < 0 ? r[0] : r[i];
+            c[i] = __shfl_sync(0xffffffffu, cnt, rr);
+            a0[i] = (lane < c[i]) ? buf[lane * ROWPITCH + rr] : EMPTY_KEY;
+            if (E == 1) {
+                a1[i] = EMPTY_KEY;
+                p[i] = (lane + 32 < c[i]) ? buf[(lane + 32) * ROWPITCH + rr] : EMPTY_KEY;
+            } else {
+                a1[i] = (lane + 32 < c[i]) ? buf[(lane + 32) * ROWPITCH + rr] : EMPTY_KEY;
+                p[i] = (lane + 64 < c[i]) ? buf[(lane + 64) * ROWPITCH + rr] : EMPTY_KEY;
             }
-            p = sort32(p, lane);
-            const unsigned long long lo1 = clean32(umin64(a1, reverse32(p)), lane);   // 32 smallest of (a1 u p); rest dropped
-            const unsigned long long rl = reverse32(lo1);
-            const unsigned long long lo = umin64(a0, rl), hi = umax64(a0, rl);
-            a0 = clean32(lo, lane);
-            a1 = clean32(hi, lane);
-            buf[lane * ROWPITCH + r] = a0;
-            buf[(lane + 32) * ROWPITCH + r] = a1;
-            lastkey = a1;
         }
-        const int keep = 32 * E;
-        const int newcnt = c < keep ? c : keep;
-        const unsigned long long last = __shfl_sync(0xffffffffu, lastkey, 31);
-        if (lane == r) {
-            cnt = newcnt;
-            sorted = true;
-            thr = (newcnt == keep) ? key_score(last) : __int_as_float(0x7f800000);
+        merge_keys<E, NR>(a0, a1, p, sort_kept, lane);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (r[i] >= 0) {   // warp-uniform
+                buf[lane * ROWPITCH + r[i]] = a0[i];
+                if (E == 2) buf[(lane + 32) * ROWPITCH + r[i]] = a1[i];
+                const int keep = 32 * E;
+                const int newcnt = c[i] < keep ? c[i] : keep;
+                const unsigned long long last = __shfl_sync(0xffffffffu, E == 1 ? a0[i] : a1[i], 31);
+                if (lane == r[i]) {
+                    cnt = newcnt;
+                    sorted = true;
+                    thr = (newcnt == keep) ? key_score(last) : __int_as_float(0x7f800000);
+                }
+            }
         }
     }
     __syncwarp();
@@ -481,16 +534,18 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], const int co
 // Two chunks behind ONE vote/branch: both min trees interleave (a lone warp per scheduler has nothing else to hide
 // the ALU latency behind) and the quiet path pays one vote instead of two.
 template <int CAPV>
-__device__ __forceinline__ void scan_pair(const uint32_t (&va)[32], const uint32_t (&vb)[32], const int col0, const float thr, int& cnt,
+__device__ __forceinline__ bool scan_pair(const uint32_t (&va)[32], const uint32_t (&vb)[32], const int col0, const float thr, int& cnt,
                                           bool& dirty, unsigned long long* __restrict__ buf, float4* __restrict__ stg, const int lane,
                                           int* stat = nullptr) {
     const float ma = chunk_min(va), mb = chunk_min(vb);
-    if (__any_sync(0xffffffffu, fminf(ma, mb) < thr)) {
+    const bool any = __any_sync(0xffffffffu, fminf(ma, mb) < thr);
+    if (any) {
         const unsigned ha = __ballot_sync(0xffffffffu, ma < thr);
         if (ha) append_hits<CAPV>(va, ha, col0, thr, cnt, dirty, buf, stg, lane, stat);
         const unsigned hb = __ballot_sync(0xffffffffu, mb < thr);
         if (hb) append_hits<CAPV>(vb, hb, col0 + 32, thr, cnt, dirty, buf, stg, lane, stat);
     }
+    return any;   // warp-uniform
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -796,7 +851,9 @@ constexpr int TS_MAX_NBOX = 4;               // A columns: 32 per box, 3*128 acc
 constexpr int TS_THREADS = 352;              // warp 0: TMA, warps 1 and 10: MMA issuers (even / odd tiles), warps 2..9: epilogue
 constexpr int TS_EPI_WARPS = 8;
 constexpr int TS_PENDW = 24;                 // pending keys per row and epilogue warp
-constexpr int TS_BOOT_TILES = 4;             // first tiles: scanned by one warp of each pair with a compaction after every chunk
+// first tiles: scanned by one warp of each pair with a compaction after every chunk; afterwards a row sees on average
+// 64 * KEEP / (128 * boot tiles) = 8 hits per 64 columns, far below the 24 pending slots of a warp
+constexpr int TS_BOOT_TILES_PER_E = 2;
 template <int E>
 struct TsCand {
     static constexpr int KEEP = 32 * E;
@@ -857,33 +914,33 @@ __device__ __forceinline__ void compact_pending(unsigned long long* __restrict__
     __syncwarp();
     pair_fence();
     if (mstat) mstat[0] += clock64() - m0;
+    constexpr int NR = MERGE_ROWS;
     while (todo) {
         long long r0 = 0;
         if (mstat) r0 = clock64();
-        const int r = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int c = __shfl_sync(0xffffffffu, pc, r);
-        unsigned long long a0 = buf[lane * ROWPITCH + r];
-        unsigned long long p = (lane < c) ? buf[(pbase + lane) * ROWPITCH + r] : EMPTY_KEY;
-        p = sort32(p, lane);
-        unsigned long long lastkey;
-        if (E == 1) {
-            a0 = clean32(umin64(a0, reverse32(p)), lane);
-            buf[lane * ROWPITCH + r] = a0;
-            lastkey = a0;
-        } else {
-            unsigned long long a1 = buf[(lane + 32) * ROWPITCH + r];
-            const unsigned long long lo1 = clean32(umin64(a1, reverse32(p)), lane);
-            const unsigned long long rl = reverse32(lo1);
-            const unsigned long long lo = umin64(a0, rl), hi = umax64(a0, rl);
-            a0 = clean32(lo, lane);
-            a1 = clean32(hi, lane);
-            buf[lane * ROWPITCH + r] = a0;
-            buf[(lane + 32) * ROWPITCH + r] = a1;
-            lastkey = a1;
+        int r[NR];
+        unsigned long long a0[NR], a1[NR], p[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            r[i] = todo ? __ffs(todo) - 1 : -1;                    // -1: batch slot unused (computed on row r[0], not stored)
+            todo &= todo - 1;
+            const int rr = r[i] < 0 ? r[0] : r[i];
+            const int c = __shfl_sync(0xffffffffu, pc, rr);
+            a0[i] = buf[lane * ROWPITCH + rr];
+            a1[i] = (E == 2) ? buf[(lane + 32) * ROWPITCH + rr] : EMPTY_KEY;
+            p[i] = (lane < c) ? buf[(pbase + lane) * ROWPITCH + rr] : EMPTY_KEY;
         }
-        if (lane == 31) thr_row[r] = (lastkey == EMPTY_KEY) ? __int_as_float(0x7f800000) : key_score(lastkey);
-        if (lane == r) pc = 0;
+        merge_keys<E, NR>(a0, a1, p, false, lane);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (r[i] >= 0) {   // warp-uniform
+                buf[lane * ROWPITCH + r[i]] = a0[i];
+                if (E == 2) buf[(lane + 32) * ROWPITCH + r[i]] = a1[i];
+                const unsigned long long lastkey = (E == 1) ? a0[i] : a1[i];
+                if (lane == 31) thr_row[r[i]] = (lastkey == EMPTY_KEY) ? __int_as_float(0x7f800000) : key_score(lastkey);
+                if (lane == r[i]) pc = 0;
+            }
+        }
         if (mstat) { const long long dt = clock64() - r0; mstat[3] += dt; if (dt < mstat[4]) mstat[4] = dt; if (dt > mstat[5]) mstat[5] = dt; }
     }
     pair_fence();
@@ -893,7 +950,10 @@ __device__ __forceinline__ void compact_pending(unsigned long long* __restrict__
 
 template <int E, int NBOX>
 __global__ void __launch_bounds__(TS_THREADS, 1)
-knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] query operand rows (global)
+knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] query operand rows (global); the first NBOX*64 columns are used
+                         const int a_pitch,
+                         const int32_t* __restrict__ qmap,  // optional: CTA row j serves query qmap[j] (second tier: the uncertified queries)
+                         const int* __restrict__ qcount,    // with qmap: number of valid entries (device side, no host sync)
                          const __grid_constant__ CUtensorMap tmB, const MmaSched sched, const int nslot, const int64_t nq,
                          const int ntiles, const int tiles_per_split,
                          int32_t* __restrict__ cand_idx,   // [nsplit][nq][32E]
@@ -904,6 +964,8 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
                          const int trace_start) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
+    const int64_t nq_eff = qcount ? (int64_t)*qcount : nq;   // rows that exist; nq stays the stride of the output arrays
+    if ((int64_t)blockIdx.x * BM >= nq_eff) return;          // whole CTA, before any barrier or TMEM allocation
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     constexpr int A_COLS = NBOX * 32;                      // TMEM columns holding the query operand
@@ -928,7 +990,12 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
     const int tile1 = min(ntiles, tile0 + tiles_per_split);
     const int my_tiles = tile1 - tile0;
     const int m0 = blockIdx.x * BM;
+#ifdef B200_TRACE   // per-warp cycle accounting of CTA (0,0): compiled in only for measurement builds (tools/build_variant.sh)
     const bool trace = dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+#else
+    constexpr bool trace = false;
+    (void)dbg_ts;
+#endif
     (void)trace_start;
     if (trace && threadIdx.x == 0) {
         unsigned long long gt;
@@ -1036,17 +1103,20 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
         bool dirty = false;
         long long acc_t[4] = {0, 0, 0, 0};   // measurement aid (trace only): tfull wait, TMEM load, scan, merge
         int stat[3] = {0, 0, 0};
-        long long pstat[4] = {0, 0, 0, 0};
         long long mstat[6] = {0, 0, 0, 0, 1LL << 60, 0};   // lock wait cycles, merge calls, merged rows, row cycles sum/min/max
         uint32_t v0[32], v1[32];
-        const int nboot = min(my_tiles, TS_BOOT_TILES);
+        const int nboot = min(my_tiles, TS_BOOT_TILES_PER_E * E);
 
         if (grp == 0) {
             // (1) this thread's query row -> TMEM (A operand of every MMA of this CTA)
-            const uint4* arow = reinterpret_cast<const uint4*>(opA + ((size_t)m0 + q4 * 32 + lane) * (NBOX * KBOX));
+            const int64_t j = (int64_t)m0 + q4 * 32 + lane;
+            int64_t src = j;                                       // rows past nq are zero padding of opA
+            if (qmap) src = (j < nq_eff) ? (int64_t)qmap[j] : -1;
+            const uint4* arow = reinterpret_cast<const uint4*>(opA + (size_t)(src < 0 ? 0 : src) * (size_t)a_pitch);
 #pragma unroll
             for (int sl = 0; sl < NBOX * 4; ++sl) {
-                const uint4 lo = __ldg(arow + 2 * sl), hi = __ldg(arow + 2 * sl + 1);
+                uint4 lo = make_uint4(0, 0, 0, 0), hi = make_uint4(0, 0, 0, 0);
+                if (src >= 0) { lo = __ldg(arow + 2 * sl); hi = __ldg(arow + 2 * sl + 1); }
                 tmem_st8(tmem_base + lane_sel + (uint32_t)(sl * 8), lo, hi);
             }
             tmem_st_wait();
@@ -1079,7 +1149,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
                 }
             }
             compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);   // every row sorted (padded with EMPTY_KEY), thresholds final
-            thr_row[lane] = thr;
+            thr_row[lane] = (dbg_mode == 8) ? __int_as_float(0xff800000) : thr;   // 8: measurement aid, no hit ever
         } else {
             for (int tl = 0; tl < nboot; ++tl) {
                 const int stage = tl % TS_STAGES;
@@ -1094,14 +1164,21 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
         int pc = 0;                                     // keys in this warp's pending segment of row `lane`
         const int pbase = KEEP + grp * TS_PENDW;
         unsigned long long* pend = mybuf + (size_t)pbase * ROWPITCH;
+        // Quiet tiles (no score below any threshold of the warp's rows -- the common case) must stay a short dependent
+        // chain: wait, two TMEM loads, release, min tree, ONE vote.  Stage/parity are carried in registers, the row
+        // threshold is re-read from shared memory only after a hit (own merge) or every 8th tile (partner's merges: a
+        // stale threshold is merely lenient), and the pending counts are only inspected after a hit.
+        int stage = nboot % TS_STAGES;
+        uint32_t par = (uint32_t)((nboot / TS_STAGES) & 1);
+        const bool skip_read = dbg_mode == 1;
+        float thr = thr_row[lane];
         for (int tl = nboot; tl < my_tiles; ++tl) {
-            const int stage = tl % TS_STAGES;
             long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (trace) c0 = clock64();
-            mbar_wait_u(smem_u32(&tfull[stage]), (uint32_t)((tl / TS_STAGES) & 1));
+            mbar_wait_u(smem_u32(&tfull[stage]), par);
             tc_fence_after();
             if (trace) c1 = clock64();
-            if (dbg_mode != 1) {
+            if (!skip_read) {
                 const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN + grp * 64);
                 tmem_ld32(tbase, v0);
                 tmem_ld32(tbase + 32u, v1);
@@ -1110,32 +1187,21 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+            if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
             if (trace) c2 = clock64();
-            if (dbg_mode == 1) continue;
-            const float thr = thr_row[lane];
-            scan_pair<TS_PENDW>(v0, v1, (tile0 + tl) * TS_BN + grp * 64, thr, pc, dirty, pend, stg, lane, trace ? stat : nullptr);
+            if (skip_read) continue;
+            const bool hit = scan_pair<TS_PENDW>(v0, v1, (tile0 + tl) * TS_BN + grp * 64, thr, pc, dirty, pend, stg, lane, trace ? stat : nullptr);
             if (trace) c3 = clock64();
-            // early tiles still see several hits per row and pair of chunks: start every pair with an empty segment
-            if (trace && (tl & 63) == 37) {   // measurement aid: in-situ latency of dependent SHFL / ALU / LDS chains
-                uint32_t x = v0[0] + lane;
-                const long long p0 = clock64();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) x = __shfl_xor_sync(0xffffffffu, x, 1 + (i & 15)) + 1u;
-                const long long p1 = clock64();
-                float f = __uint_as_float(v0[1]);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) f = fminf(f * 1.0001f, 100.f + (float)i);
-                const long long p2 = clock64();
-                uint32_t y = lane;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) y = reinterpret_cast<volatile uint32_t*>(stg)[(y + x) & 255] & 255u;
-                const long long p3 = clock64();
-                pstat[0] += p1 - p0; pstat[1] += p2 - p1; pstat[2] += p3 - p2; pstat[3] += 1;
-                if (x == 0x1234567u && f == 3.f && y == 999u) dirty = true;
+            const bool last = tl == my_tiles - 1;
+            if (hit || last) {   // warp-uniform
+                // early tiles still see several hits per row and pair of chunks: start every pair with an empty segment
+                const int limit = (last || tl < 32) ? 0 : TS_PENDW / 2;
+                const unsigned todo = __ballot_sync(0xffffffffu, pc > limit);
+                if (todo) compact_pending<E>(mybuf, pbase, lane, todo, pc, thr_row, lock, trace ? mstat : nullptr);
+                thr = thr_row[lane];
+            } else if ((tl & 7) == 0) {
+                thr = thr_row[lane];
             }
-            const int limit = (tl == my_tiles - 1 || tl < 32) ? 0 : TS_PENDW / 2;
-            const unsigned todo = __ballot_sync(0xffffffffu, pc > limit);
-            if (todo) compact_pending<E>(mybuf, pbase, lane, todo, pc, thr_row, lock, trace ? mstat : nullptr);
             if (trace) {
                 acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; acc_t[2] += c3 - c2; acc_t[3] += clock64() - c3;
             }
@@ -1148,7 +1214,6 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
             for (int i = 0; i < 3; ++i) dbg_ts[(warp - 2) * 8 + 4 + i] = stat[i];
             dbg_ts[(warp - 2) * 8 + 7] = my_tiles - nboot;
             for (int i = 0; i < 6; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = mstat[i];
-            for (int i = 0; i < 4; ++i) dbg_ts[128 + (warp - 2) * 4 + i] = pstat[i];
         }
         // (4) output: the two warps of a pair write 16 rows each
         const int64_t rowbase = (int64_t)m0 + q4 * 32;
@@ -1156,7 +1221,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
 #pragma unroll 1
         for (int r = grp * 16; r < grp * 16 + 16; ++r) {
             const int64_t row = rowbase + r;
-            if (row < nq) {
+            if (row < nq_eff) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const unsigned long long key = mybuf[(lane + 32 * e) * ROWPITCH + r];
@@ -1166,7 +1231,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][NBOX*64] 
                 }
             }
         }
-        if (grp == 0 && rowbase + lane < nq) thr_out[sbase + rowbase + lane] = dirty_row[lane] ? __int_as_float(0xff800000) : thr_row[lane];
+        if (grp == 0 && rowbase + lane < nq_eff) thr_out[sbase + rowbase + lane] = dirty_row[lane] ? __int_as_float(0xff800000) : thr_row[lane];
         tc_fence_before();
     }
     __syncthreads();
@@ -1245,7 +1310,10 @@ __device__ __forceinline__ void split_half(double xs, __half& hi, __half& lo) {
 
 template <bool IS_QUERY>
 __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int64_t n_pad, int d, KLayout L,
-                                    const int* __restrict__ scale_exp, __half* __restrict__ op, const double* __restrict__ norm_f64) {
+                                    const int* __restrict__ scale_exp, __half* __restrict__ op, const double* __restrict__ norm_f64,
+                                    float2* __restrict__ qerr,            // queries: (|a - ah|, |ah|) over the full-group dims, rounded up
+                                    unsigned int* __restrict__ bmax_bits  // references: max |bh| and max |b - bh| (float bits, rounded up)
+                                    ) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     const int KS = L.nbox * KBOX;
@@ -1268,19 +1336,33 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
     const double S = scalbn(1.0, *scale_exp);
     const double mul = IS_QUERY ? -2.0 * S : S;
     const double* x = X + i * d;
+    double hi2 = 0.0, lo2 = 0.0;   // squared norms of the hi parts and of the exact residuals (what the one-term schedule drops)
     for (int g = 0; g < L.groups; ++g) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int t = g * 16 + j;
             const double xv = (t < d) ? x[t] : 0.0;
             split_half(xv * mul, hbuf[j], lbuf[j]);
+            const double hv = (double)__half2float(hbuf[j]);
+            const double rv = xv * mul - hv;
+            hi2 += hv * hv;
+            lo2 += rv * rv;
         }
         const uint4* hp = reinterpret_cast<const uint4*>(hbuf);
         const uint4* lp = reinterpret_cast<const uint4*>(lbuf);
-        row[(2 * g) * 2 + 0] = hp[0];
-        row[(2 * g) * 2 + 1] = hp[1];
-        row[(2 * g + 1) * 2 + 0] = lp[0];
-        row[(2 * g + 1) * 2 + 1] = lp[1];
+        row[g * 2 + 0] = hp[0];
+        row[g * 2 + 1] = hp[1];
+        row[(L.nprim + g) * 2 + 0] = lp[0];
+        row[(L.nprim + g) * 2 + 1] = lp[1];
+    }
+    {
+        const float fh = __double2float_ru(sqrt(hi2) * 1.0000001), fl = __double2float_ru(sqrt(lo2) * 1.0000001);
+        if (IS_QUERY) {
+            if (qerr) qerr[i] = make_float2(fl, fh);
+        } else if (bmax_bits) {   // non-negative floats order like their bit patterns
+            atomicMax(bmax_bits + 0, __float_as_uint(fh));
+            atomicMax(bmax_bits + 1, __float_as_uint(fl));
+        }
     }
     // norm columns: constants on the query side, the split scaled norm on the reference side
     __half nc[3];
@@ -1296,7 +1378,7 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
         const double r2 = r1 - (double)__half2float(nc[1]) * 16.0;
         nc[2] = __double2half(r2 * 128.0);                                      // r2 / 2^-7
     }
-    int written = 2 * L.groups;
+    int written = L.groups;
     if (L.rem_slice >= 0) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) hbuf[j] = __float2half(0.f);
@@ -1323,7 +1405,8 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
         row[written * 2 + 1] = hp[1];
         ++written;
     }
-    for (int sl = written; sl < L.nbox * 4; ++sl) { row[sl * 2 + 0] = make_uint4(0, 0, 0, 0); row[sl * 2 + 1] = make_uint4(0, 0, 0, 0); }
+    // written == L.nprim here; the lo slices follow, the rest of the last box is zero
+    for (int sl = L.nslices; sl < L.nbox * 4; ++sl) { row[sl * 2 + 0] = make_uint4(0, 0, 0, 0); row[sl * 2 + 1] = make_uint4(0, 0, 0, 0); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1340,11 +1423,15 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
               const int32_t* __restrict__ cand_idx, const float* __restrict__ thr, int nsplit, int ncand_per_split,
               const int* __restrict__ scale_exp, const double* __restrict__ qnorm, const unsigned long long* __restrict__ maxnorm_bits,
               int32_t* __restrict__ out_idx, double* __restrict__ out_dist, int* __restrict__ flag_count, int32_t* __restrict__ flag_list,
-              double* __restrict__ dbg_d2 /* [nq][ncand] or null */) {
+              double* __restrict__ dbg_d2 /* [nq][ncand] or null */,
+              const int32_t* __restrict__ qmap, const int* __restrict__ qcount,   // optional: list slot j holds query qmap[j], j < *qcount
+              const int fast /* candidates came from the one-term schedule: wider error bound */,
+              const float2* __restrict__ qerr, const unsigned int* __restrict__ bmax_bits) {
     __shared__ double stage[RR_WARPS][32][RR_DCH + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
-    if (q >= nq) return;
+    const int64_t jq = (int64_t)blockIdx.x * RR_WARPS + warp;   // slot in the candidate / threshold arrays
+    if (jq >= (qcount ? (int64_t)*qcount : nq)) return;
+    const int64_t q = qmap ? (int64_t)qmap[jq] : jq;            // the query itself
     const int ncand = nsplit * ncand_per_split;
     const int rounds = ncand / 32;
     double cd[RR_MAXROUNDS];
@@ -1358,7 +1445,7 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
         if (r < rounds) {
             const int c = r * 32 + lane;
             const int sp = c / ncand_per_split, within = c % ncand_per_split;
-            const int id = cand_idx[((int64_t)sp * nq + q) * ncand_per_split + within];
+            const int id = cand_idx[((int64_t)sp * nq + jq) * ncand_per_split + within];
             ci[r] = id;
             double acc = 0.0;
             for (int t0 = 0; t0 < d; t0 += RR_DCH) {
@@ -1376,7 +1463,7 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
                 __syncwarp();
             }
             cd[r] = (id >= 0) ? acc : INFINITY;
-            if (dbg_d2) dbg_d2[q * ncand + c] = cd[r];
+            if (dbg_d2) dbg_d2[jq * ncand + c] = cd[r];
         }
     }
     // k rounds of warp arg-min under (distance, index)
@@ -1409,13 +1496,21 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
     // certificate: every non-candidate j has score_j >= min_split thr, and |score_j/S^2 + ||q||^2 - d2_j| <= eps
     if (lane == 0) {
         float tmin = __int_as_float(0x7f800000);
-        for (int sp = 0; sp < nsplit; ++sp) tmin = fminf(tmin, thr[(int64_t)sp * nq + q]);
+        for (int sp = 0; sp < nsplit; ++sp) tmin = fminf(tmin, thr[(int64_t)sp * nq + jq]);
         bool ok = true;
         if (tmin < __int_as_float(0x7f800000)) {
             const double inv = scalbn(1.0, -2 * (*scale_exp));
             const double qn = qnorm[q];
             const double M2 = __longlong_as_double((long long)*maxnorm_bits);
-            const double eps = 1.52587890625e-05 * (sqrt(qn * M2) + M2);  // 2^-16 (|q| M + M^2)
+            double eps = 1.52587890625e-05 * (sqrt(qn * M2) + M2);  // 2^-16 (|q| M + M^2)
+            // one-term schedule: with a = ah + ra, b = bh + rb over the full-group dims (ra, rb the exact residuals) the score
+            // lacks ra.bh + ah.rb + ra.rb, so |error| <= |ra||bh| + |ah||rb| + |ra||rb| (Cauchy-Schwarz) with |ra|, |ah| of
+            // THIS query and the maxima of |bh|, |rb| over the references -- all measured by the operand kernels.
+            if (fast) {
+                const float2 qe = qerr[q];
+                const double BH = (double)__uint_as_float(bmax_bits[0]), BL = (double)__uint_as_float(bmax_bits[1]);
+                eps += ((double)qe.x * BH + (double)qe.y * BL + (double)qe.x * BL) * inv * 1.001;
+            }
             const double bound = (double)tmin * inv + qn - eps;
             ok = dk < bound;
         }
@@ -1488,11 +1583,12 @@ rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict_
     }
 }
 
-__global__ void write_stats_kernel(const int* __restrict__ flag_count, int64_t* __restrict__ stats, int64_t lists, int64_t path) {
-    stats[0] = flag_count ? *flag_count : 0;
+__global__ void write_stats_kernel(const int* __restrict__ flag_count, int64_t* __restrict__ stats, int64_t lists, int64_t path,
+                                   const int* __restrict__ tier2_count = nullptr) {
+    stats[0] = flag_count ? *flag_count : 0;      // queries answered by the exact rescue kernel
     stats[1] = lists;
-    stats[2] = path;
-    stats[3] = 0;
+    stats[2] = path;                              // 1: tensor path
+    stats[3] = tier2_count ? *tier2_count : 0;    // queries the one-term tier could not certify (re-scored with three terms)
 }
 
 // squared distance debug view: cand score -> unscaled approximate squared distance
@@ -1639,7 +1735,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     }
 
     const KLayout L = make_layout(d);
-    const MmaSched sched = make_sched(L);
+    const MmaSched sched = make_sched(L, false);
     const int KS = L.nbox * KBOX;
     const int E = (k <= 24) ? 1 : 2;
     const int per = 32 * E;
@@ -1665,12 +1761,16 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     float* cand_score = dbg ? ws.get<float>((size_t)nsplit * nq * per) : nullptr;
     float* thr = ws.get<float>((size_t)nsplit * nq);
     int32_t* flag_list = ws.get<int32_t>((size_t)nq);
+    int32_t* flag_list2 = ws.get<int32_t>((size_t)nq);
+    float2* qerr = ws.get<float2>((size_t)nq_pad);
     unsigned char* scalars = ws.get<unsigned char>(64);
     if (!ws.ok()) return B200MNN_ENOMEM;
     unsigned int* absmax_bits = reinterpret_cast<unsigned int*>(scalars);
     int* scale_exp = reinterpret_cast<int*>(scalars + 8);
     unsigned long long* maxnorm_bits = reinterpret_cast<unsigned long long*>(scalars + 16);
     int* flag_count = reinterpret_cast<int*>(scalars + 24);
+    int* flag_count2 = reinterpret_cast<int*>(scalars + 28);
+    unsigned int* bmax_bits = reinterpret_cast<unsigned int*>(scalars + 32);   // [2]
     B200_CUDA(cudaMemsetAsync(scalars, 0, 64, stream));
 
     rowstat_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(dX, n, d, xnorm, absmax_bits, maxnorm_bits);
@@ -1679,9 +1779,9 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     B200_LAUNCH_CHECK();
     scale_kernel<<<1, 1, 0, stream>>>(absmax_bits, maxnorm_bits, scale_exp);
     B200_LAUNCH_CHECK();
-    prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm);
+    prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm, nullptr, bmax_bits);
     B200_LAUNCH_CHECK();
-    prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr);
+    prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr, qerr, nullptr);
     B200_LAUNCH_CHECK();
 
     // Thread-block clusters (optional, B200MNN_CLUSTER=2|4): the CTAs of a cluster work on different query tiles against
@@ -1701,51 +1801,66 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     int dev = 0, max_smem = 0;
     B200_CUDA(cudaGetDevice(&dev));
     B200_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    int nslot = MAX_SLOTS;
-    size_t smem = 0;
-    if (use_ts) {
-        while (nslot > L.nbox + 1 && ts_smem_bytes(nslot, E) > (size_t)max_smem) --nslot;
-        smem = ts_smem_bytes(nslot, E);
-    } else {
-        while (nslot > 3 && candidates_smem_bytes(L.nbox, nslot, E) > (size_t)max_smem) --nslot;
-        smem = candidates_smem_bytes(L.nbox, nslot, E);
-    }
-    if (smem > (size_t)max_smem) return fail(B200MNN_ECUDA, "device does not offer enough shared memory per block for the kNN kernel");
-    const char* dbg_env = getenv("B200MNN_DEBUG_MODE");   // measurement aid only (results are wrong when non-zero)
+    const char* dbg_env = getenv("B200MNN_DEBUG_MODE");   // measurement aid only (results are void when non-zero)
     const int dbg_mode = dbg_env ? atoi(dbg_env) : 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(g_prof_mu);
-        if (g_prof_on) {
-            B200_CUDA(cudaEventCreate(&ev0));
-            B200_CUDA(cudaEventCreate(&ev1));
-            B200_CUDA(cudaEventRecord(ev0, stream));
-        }
-    }
     long long* dbg_ts = nullptr;
     const int trace_start = getenv("B200MNN_TRACE") ? atoi(getenv("B200MNN_TRACE")) : 0;
-    if (getenv("B200MNN_TRACE")) {  // measurement aid: per-tile clock64 trace of CTA (0,0), printed after the launch
+    if (getenv("B200MNN_TRACE")) {  // measurement aid: cycle accounting of CTA (0,0), printed after the launch
         dbg_ts = ws.get<long long>(64 * 32 + 64);
         if (!dbg_ts) return B200MNN_ENOMEM;
-        B200_CUDA(cudaMemsetAsync(dbg_ts, 0, sizeof(long long) * (64 * 32 + 64), stream));
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)round_up(mtiles, csize), (unsigned)nsplit, 1);   // padding CTAs see only zero-filled query rows
-    cfg.blockDim = dim3(use_ts ? TS_THREADS : NUM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)csize;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const int64_t nq_c = nq;
+    // Two tiers (TS variant only).  Tier 1 scores every query with the ONE-term schedule (2.5x fewer MMAs, half the
+    // operand traffic at d = 50); its re-rank certifies with the correspondingly wider error bound.  Queries it cannot
+    // certify are scored again by the three-term schedule (tier 2, reading its query rows through the flag list --
+    // no host synchronisation, surplus CTAs exit at once), and what even that cannot certify goes to the exact
+    // rescue kernel.  B200MNN_TIERS=1 (or a layout with no full 16-dim group) runs the three-term schedule alone.
+    const char* tenv = getenv("B200MNN_TIERS");
+    // The one-term tier certifies a query when its k-th distance clears the KEEP-th best score by the error bound:
+    // worthwhile while k leaves a third of the kept candidates as margin.
+    const bool two_tier = use_ts && !dbg && L.groups > 0 && 3 * k <= 2 * per && !(tenv && atoi(tenv) == 1);
+
+    auto launch_candidates = [&](bool fast, const int32_t* qmap, const int* qcount) -> int {
+        const MmaSched sch = make_sched(L, fast);
+        const int nb = fast ? L.nbox_fast : L.nbox;
+        int nslot = MAX_SLOTS;
+        size_t smem = 0;
+        if (use_ts) {
+            while (nslot > nb + 1 && ts_smem_bytes(nslot, E) > (size_t)max_smem) --nslot;
+            smem = ts_smem_bytes(nslot, E);
+        } else {
+            while (nslot > 3 && candidates_smem_bytes(nb, nslot, E) > (size_t)max_smem) --nslot;
+            smem = candidates_smem_bytes(nb, nslot, E);
+        }
+        if (smem > (size_t)max_smem) return fail(B200MNN_ECUDA, "device does not offer enough shared memory per block for the kNN kernel");
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_prof_mu);
+            if (g_prof_on) {
+                B200_CUDA(cudaEventCreate(&ev0));
+                B200_CUDA(cudaEventCreate(&ev1));
+                B200_CUDA(cudaEventRecord(ev0, stream));
+            }
+        }
+        if (dbg_ts) B200_CUDA(cudaMemsetAsync(dbg_ts, 0, sizeof(long long) * (64 * 32 + 64), stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)round_up(mtiles, csize), (unsigned)nsplit, 1);   // padding CTAs see only zero-filled query rows
+        cfg.blockDim = dim3(use_ts ? TS_THREADS : NUM_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const int64_t nq_c = nq;
+        const __half* opA_c = opA;
+        const int a_pitch = KS;
 #define B200_LAUNCH_CAND(EE, NB)                                                                                              \
     do {                                                                                                                       \
         B200_CUDA(cudaFuncSetAttribute(knn_candidates_kernel<EE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_kernel<EE, NB>, tmA, tmB, sched, nslot, nq_c, ntiles,                 \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_kernel<EE, NB>, tmA, tmB, sch, nslot, nq_c, ntiles,                   \
                                      tiles_per_split, cand_idx, cand_score, thr, dbg_mode, csize, dbg_ts, trace_start));       \
     } while (0)
 #define B200_LAUNCH_CAND_E(NB)               \
@@ -1756,74 +1871,80 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
 #define B200_LAUNCH_TS(EE, NB)                                                                                                   \
     do {                                                                                                                          \
         B200_CUDA(cudaFuncSetAttribute(knn_candidates_ts_kernel<EE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_ts_kernel<EE, NB>, opA_c, tmB, sched, nslot, nq_c, ntiles,               \
-                                     tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start));                 \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_ts_kernel<EE, NB>, opA_c, a_pitch, qmap, qcount, tmB, sch, nslot, nq_c,  \
+                                     ntiles, tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start));         \
     } while (0)
 #define B200_LAUNCH_TS_E(NB)               \
     do {                                   \
         if (E == 1) B200_LAUNCH_TS(1, NB); \
         else B200_LAUNCH_TS(2, NB);        \
     } while (0)
-    const __half* opA_c = opA;
-    if (use_ts) {
-        switch (L.nbox) {
-            case 1: B200_LAUNCH_TS_E(1); break;
-            case 2: B200_LAUNCH_TS_E(2); break;
-            case 3: B200_LAUNCH_TS_E(3); break;
-            default: B200_LAUNCH_TS_E(4); break;
+        if (use_ts) {
+            switch (nb) {
+                case 1: B200_LAUNCH_TS_E(1); break;
+                case 2: B200_LAUNCH_TS_E(2); break;
+                case 3: B200_LAUNCH_TS_E(3); break;
+                default: B200_LAUNCH_TS_E(4); break;
+            }
+        } else {
+            switch (nb) {
+                case 1: B200_LAUNCH_CAND_E(1); break;
+                case 2: B200_LAUNCH_CAND_E(2); break;
+                case 3: B200_LAUNCH_CAND_E(3); break;
+                case 4: B200_LAUNCH_CAND_E(4); break;
+                case 5: B200_LAUNCH_CAND_E(5); break;
+                default: B200_LAUNCH_CAND_E(6); break;
+            }
         }
-    } else
-    switch (L.nbox) {
-        case 1: B200_LAUNCH_CAND_E(1); break;
-        case 2: B200_LAUNCH_CAND_E(2); break;
-        case 3: B200_LAUNCH_CAND_E(3); break;
-        case 4: B200_LAUNCH_CAND_E(4); break;
-        case 5: B200_LAUNCH_CAND_E(5); break;
-        default: B200_LAUNCH_CAND_E(6); break;
-    }
 #undef B200_LAUNCH_CAND_E
 #undef B200_LAUNCH_CAND
 #undef B200_LAUNCH_TS_E
 #undef B200_LAUNCH_TS
-    B200_LAUNCH_CHECK();
-    if (dbg_ts) {
-        static long long h[64 * 32 + 64];
-        B200_CUDA(cudaMemcpyAsync(h, dbg_ts, sizeof(h), cudaMemcpyDeviceToHost, stream));
-        B200_CUDA(cudaStreamSynchronize(stream));
-        if (use_ts) {
-            if (h[194] > h[192])
-                fprintf(stderr, "CTA (0,0): %lld cycles in %.1f us -> SM clock %.0f MHz while this kernel ran\n", h[195] - h[193], (h[194] - h[192]) / 1e3,
-                        (double)(h[195] - h[193]) / ((h[194] - h[192]) / 1e3));
-            for (int w = 0; w < TS_EPI_WARPS; ++w) {
-                const long long* a = h + w * 8;
-                const double nt = a[7] ? (double)a[7] : 1.0;
-                fprintf(stderr, "epilogue warp %d (%s half), cycles/tile: tfull wait %.0f, TMEM load %.0f, scan %.0f, merge %.0f; %lld tiles, %lld hit chunks, %lld hit rows, %lld keys\n",
-                        w, w < 4 ? "left" : "right", a[0] / nt, a[1] / nt, a[2] / nt, a[3] / nt, a[7], a[4], a[5], a[6]);
-                const long long* m = h + 64 + w * 8;
-                fprintf(stderr, "    merges: %lld calls, %lld rows, lock wait %.0f cycles/call; cycles per row: mean %.0f min %lld max %lld\n", m[1], m[2],
-                        m[1] ? (double)m[0] / m[1] : 0.0, m[2] ? (double)m[3] / m[2] : 0.0, m[4], m[5]);
-                const long long* ps = h + 128 + w * 4;
-                if (ps[3]) fprintf(stderr, "    in-situ dependent-chain latency: SHFL+IADD %.1f, FMUL+FMNMX %.1f, LDS %.1f cycles/op (%lld probes)\n",
-                                   (double)ps[0] / (32.0 * ps[3]), (double)ps[1] / (32.0 * ps[3]), (double)ps[2] / (16.0 * ps[3]), ps[3]);
-            }
-        } else {
-            const long long t00 = h[0];
-            fprintf(stderr, "tile: mma[wait_tempty got_tempty got_full0 issued0 got_full1 issued1] epi[wait_tfull got_tfull released done] (cycles rel.)\n");
-            for (int t = 0; t < 24; ++t) {
-                fprintf(stderr, "%5d:", t + trace_start);
-                for (int k2 = 0; k2 < 12; ++k2) if (k2 < 6 || k2 >= 8) fprintf(stderr, " %7lld", h[t * 32 + k2] ? h[t * 32 + k2] - t00 : -1LL);
-                fprintf(stderr, "  chunks:");
-                for (int k2 = 16; k2 < 24; ++k2) fprintf(stderr, " %5lld", h[t * 32 + k2] ? h[t * 32 + k2] - h[t * 32 + 9] : -1LL);
-                fprintf(stderr, " cnt0=%lld cnt1=%lld\n", h[t * 32 + 24], h[t * 32 + 25]);
+        B200_LAUNCH_CHECK();
+        if (ev0) {
+            B200_CUDA(cudaEventRecord(ev1, stream));
+            std::lock_guard<std::mutex> lock(g_prof_mu);
+            g_prof_events.emplace_back(ev0, ev1);
+            if (!qmap) g_prof_flops += 2.0 * (double)nq * (double)n * (double)d;   // algorithmic flops of the call, counted once
+        }
+        if (dbg_ts) {
+            static long long h[64 * 32 + 64];
+            B200_CUDA(cudaMemcpyAsync(h, dbg_ts, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            B200_CUDA(cudaStreamSynchronize(stream));
+            fprintf(stderr, "--- %s schedule, %d box(es) per tile, %d slots ---\n", fast ? "one-term" : "three-term", nb, nslot);
+            if (use_ts) {
+                if (h[194] > h[192])
+                    fprintf(stderr, "CTA (0,0): %lld cycles in %.1f us -> SM clock %.0f MHz while this kernel ran\n", h[195] - h[193], (h[194] - h[192]) / 1e3,
+                            (double)(h[195] - h[193]) / ((h[194] - h[192]) / 1e3));
+                for (int w = 0; w < TS_EPI_WARPS; ++w) {
+                    const long long* a = h + w * 8;
+                    const double nt = a[7] ? (double)a[7] : 1.0;
+                    fprintf(stderr, "epilogue warp %d (%s half), cycles/tile: tfull wait %.0f, TMEM load %.0f, scan %.0f, merge %.0f; %lld tiles, %lld hit chunks, %lld hit rows, %lld keys\n",
+                            w, w < 4 ? "left" : "right", a[0] / nt, a[1] / nt, a[2] / nt, a[3] / nt, a[7], a[4], a[5], a[6]);
+                    const long long* m = h + 64 + w * 8;
+                    fprintf(stderr, "    merges: %lld calls, %lld rows, lock wait %.0f cycles/call; cycles per batch: mean %.0f min %lld max %lld\n", m[1], m[2],
+                            m[1] ? (double)m[0] / m[1] : 0.0, m[2] ? (double)m[3] / m[2] : 0.0, m[4], m[5]);
+                    const long long* ps = h + 128 + w * 4;
+                    if (ps[3]) fprintf(stderr, "    in-situ dependent-chain latency: SHFL+IADD %.1f, LDS %.1f cycles/op (%lld probes)\n",
+                                       (double)ps[0] / (32.0 * ps[3]), (double)ps[2] / (16.0 * ps[3]), ps[3]);
+                }
+            } else {
+                const long long t00 = h[0];
+                fprintf(stderr, "tile: mma[wait_tempty got_tempty got_full0 issued0 got_full1 issued1] epi[wait_tfull got_tfull released done] (cycles rel.)\n");
+                for (int t = 0; t < 24; ++t) {
+                    fprintf(stderr, "%5d:", t + trace_start);
+                    for (int k2 = 0; k2 < 12; ++k2) if (k2 < 6 || k2 >= 8) fprintf(stderr, " %7lld", h[t * 32 + k2] ? h[t * 32 + k2] - t00 : -1LL);
+                    fprintf(stderr, "  chunks:");
+                    for (int k2 = 16; k2 < 24; ++k2) fprintf(stderr, " %5lld", h[t * 32 + k2] ? h[t * 32 + k2] - h[t * 32 + 9] : -1LL);
+                    fprintf(stderr, " cnt0=%lld cnt1=%lld\n", h[t * 32 + 24], h[t * 32 + 25]);
+                }
             }
         }
-    }
-    if (ev0) {
-        B200_CUDA(cudaEventRecord(ev1, stream));
-        std::lock_guard<std::mutex> lock(g_prof_mu);
-        g_prof_events.emplace_back(ev0, ev1);
-        g_prof_flops += 2.0 * (double)nq * (double)n * (double)d;
-    }
+        return 0;
+    };
+
+    const bool fast_only_env = tenv && atoi(tenv) == 3;   // measurement aid: tier 1 only (uncertified queries go straight to the rescue)
+    B200_TRY(launch_candidates(two_tier, nullptr, nullptr));
 
     if (dbg) {
         const int64_t ncand = (int64_t)nsplit * per;
@@ -1841,12 +1962,27 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         B200_CUDA(cudaMemsetAsync(d_dist, 0, sizeof(double) * (size_t)nq * k, stream));
         return 0;
     }
-    rerank_kernel<<<(unsigned)ceil_div(nq, RR_WARPS), RR_WARPS * 32, 0, stream>>>(dX, dQ, nq, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm,
-                                                                                maxnorm_bits, d_idx, d_dist, flag_count, flag_list, nullptr);
+    const unsigned rr_grid = (unsigned)ceil_div(nq, RR_WARPS);
+    rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nq, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
+                                                         d_dist, flag_count, flag_list, nullptr, nullptr, nullptr, two_tier ? 1 : 0, qerr, bmax_bits);
     B200_LAUNCH_CHECK();
-    rescue_kernel<<<sm_count() * 4, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, k, flag_count, flag_list, nq, d_idx, d_dist);
+    const int* rescue_count = flag_count;
+    const int32_t* rescue_list = flag_list;
+    if (two_tier && !fast_only_env) {
+        // tier 2: the flagged queries again, three-term schedule, same grid (CTAs past the flag count exit immediately)
+        B200_TRY(launch_candidates(false, flag_list, flag_count));
+        rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nq, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
+                                                             d_dist, flag_count2, flag_list2, nullptr, flag_list, flag_count, 0, qerr, bmax_bits);
+        B200_LAUNCH_CHECK();
+        rescue_count = flag_count2;
+        rescue_list = flag_list2;
+    }
+    rescue_kernel<<<sm_count() * 4, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, k, rescue_count, rescue_list, nq, d_idx, d_dist);
     B200_LAUNCH_CHECK();
-    if (d_stats) { write_stats_kernel<<<1, 1, 0, stream>>>(flag_count, d_stats, nsplit, 1); B200_LAUNCH_CHECK(); }
+    if (d_stats) {
+        write_stats_kernel<<<1, 1, 0, stream>>>(rescue_count, d_stats, nsplit, 1, two_tier ? flag_count : nullptr);
+        B200_LAUNCH_CHECK();
+    }
     return 0;
 }
 
