@@ -1,0 +1,453 @@
+// Cluster plan for the pruned exact kNN search (see knn_cluster.cuh).
+//
+// Exactness never depends on the quality of the clustering.  For a query q assigned to centroid A and a reference
+// cluster B (centroid c_B), let u = (c_B - c_A) / |c_B - c_A|.  Every reference x of B satisfies
+//     |q - x| >= u.(x - q) = u.x - u.q >= min_{x in B} u.x - u.q                       (Cauchy-Schwarz),
+// so with  ext_B(A) = max_{x in B} (x.c_A - x.c_B) / |c_B - c_A|   (how far B reaches towards A, = -min u.x) and
+// v_q(B) = (q.c_B - q.c_A) / |c_B - c_A| (= u.q) the bound is  LB(q, B) = -ext_B(A) - v_q(B).  A tile of 128 queries
+// takes the minimum over its rows.  All of it is computed in double with an explicit rounding margin; the scoring
+// kernel skips a cluster only when S^2 LB^2 exceeds the current threshold score of EVERY row of the tile, which is
+// exactly the condition under which the re-rank certificate (knn_tc.cu) treats an unseen reference like a rejected one.
+//
+// The k-means itself (farthest-point seeds + a few Lloyd steps on a strided sample) uses floating-point atomics, so
+// centroids may differ in the last bits from run to run; only the amount of skipped work can depend on that.
+#include "knn_cluster.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace b200 {
+namespace knn {
+
+namespace {
+
+constexpr int SAMPLE_MAX = 16384;   // rows of the k-means sample
+constexpr int FPS_MAX = 4096;       // rows used by the farthest-point seeding
+constexpr int LLOYD_ITERS = 4;
+
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    const long long b = (k & 0x8000000000000000ull) ? (long long)(k & 0x7fffffffffffffffull) : (long long)~k;
+    return __longlong_as_double(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k-means on a strided sample
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gather_sample_kernel(const double* __restrict__ X, int64_t n, int d, int m, double* __restrict__ S) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)m * d) return;
+    const int64_t i = e / d;
+    const int t = (int)(e - i * d);
+    S[e] = X[((i * n) / m) * d + t];
+}
+
+// Farthest-point seeding over every (m / mf)-th sample row: one block, one warp per row and step.
+__global__ void __launch_bounds__(1024) fps_seed_kernel(const double* __restrict__ S, int m, int d, int mf, int C, double* cen) {
+    __shared__ double mind[FPS_MAX];
+    __shared__ double wv[32];
+    __shared__ int wi[32];
+    __shared__ int pick;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int step = m / mf;
+    for (int i = tid; i < mf; i += 1024) mind[i] = INFINITY;
+    if (tid == 0) pick = 0;
+    __syncthreads();
+    for (int j = 0; j < C; ++j) {
+        const double* src = S + (size_t)pick * step * d;
+        for (int t = tid; t < d; t += 1024) cen[(size_t)j * d + t] = src[t];
+        __syncthreads();
+        if (j == C - 1) break;
+        const double* cj = cen + (size_t)j * d;
+        double bv = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = warp; i < mf; i += 32) {
+            const double* x = S + (size_t)i * step * d;
+            double acc = 0.0;
+            for (int t = lane; t < d; t += 32) { const double df = x[t] - cj[t]; acc += df * df; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            const double v = fmin(mind[i], acc);
+            if (lane == 0) mind[i] = v;
+            if (v > bv) { bv = v; bi = i; }
+        }
+        if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double fv = wv[0];
+            int fi = wi[0];
+            for (int w = 1; w < 32; ++w)
+                if (wv[w] > fv || (wv[w] == fv && wi[w] < fi)) { fv = wv[w]; fi = wi[w]; }
+            pick = (fi == 0x7fffffff) ? 0 : fi;
+        }
+        __syncthreads();
+    }
+}
+
+// Nearest centroid of one row held in shared memory (pitch-free pointer), 4 centroids per pass.
+__device__ __forceinline__ int nearest_centroid(const double* __restrict__ x, int d, int C, const double* __restrict__ cen,
+                                                const double* __restrict__ cnorm) {
+    double best = INFINITY;
+    int bi = 0;
+    for (int c0 = 0; c0 < C; c0 += 4) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double* p0 = cen + (size_t)c0 * d;
+        const double* p1 = p0 + d;
+        const double* p2 = p1 + d;
+        const double* p3 = p2 + d;
+        for (int t = 0; t < d; ++t) {
+            const double xv = x[t];
+            a0 = fma(xv, __ldg(p0 + t), a0);
+            a1 = fma(xv, __ldg(p1 + t), a1);
+            a2 = fma(xv, __ldg(p2 + t), a2);
+            a3 = fma(xv, __ldg(p3 + t), a3);
+        }
+        const double s0 = cnorm[c0] - 2.0 * a0, s1 = cnorm[c0 + 1] - 2.0 * a1, s2 = cnorm[c0 + 2] - 2.0 * a2, s3 = cnorm[c0 + 3] - 2.0 * a3;
+        if (s0 < best) { best = s0; bi = c0; }
+        if (s1 < best) { best = s1; bi = c0 + 1; }
+        if (s2 < best) { best = s2; bi = c0 + 2; }
+        if (s3 < best) { best = s3; bi = c0 + 3; }
+    }
+    return bi;
+}
+
+__global__ void centroid_norm_kernel(const double* __restrict__ cen, int C, int d, double* __restrict__ cnorm) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0;
+    for (int t = 0; t < d; ++t) s = fma(cen[(size_t)c * d + t], cen[(size_t)c * d + t], s);
+    cnorm[c] = s;
+}
+
+// Stages 128 consecutive rows (row-major, d doubles each) into shared memory with an odd pitch.
+__device__ __forceinline__ void stage_rows(const double* __restrict__ X, int64_t row0, int64_t nrows, int d, int dp, double* rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r = warp; r < CL_TILE; r += nw) {
+        const int64_t i = row0 + r;
+        for (int t = lane; t < d; t += 32) rows[r * dp + t] = (i < nrows) ? X[i * d + t] : 0.0;
+    }
+}
+
+// One Lloyd step on the sample: nearest centroid, then sums / counts by atomics.
+__global__ void __launch_bounds__(CL_TILE) lloyd_accum_kernel(const double* __restrict__ S, int m, int d, int dp, int C,
+                                                            const double* __restrict__ cen, const double* __restrict__ cnorm,
+                                                            double* __restrict__ sums, int* __restrict__ counts) {
+    extern __shared__ double rows[];
+    const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
+    stage_rows(S, row0, m, d, dp, rows);
+    __syncthreads();
+    const int64_t i = row0 + threadIdx.x;
+    if (i >= m) return;
+    const double* x = rows + threadIdx.x * dp;
+    const int c = nearest_centroid(x, d, C, cen, cnorm);
+    for (int t = 0; t < d; ++t) atomicAdd(sums + (size_t)c * d + t, x[t]);
+    atomicAdd(counts + c, 1);
+}
+
+__global__ void lloyd_update_kernel(double* __restrict__ cen, int C, int d, double* __restrict__ sums, int* __restrict__ counts) {
+    const int c = blockIdx.x;
+    const int cnt = counts[c];
+    for (int t = threadIdx.x; t < d; t += blockDim.x) {
+        if (cnt > 0) cen[(size_t)c * d + t] = sums[(size_t)c * d + t] / (double)cnt;
+        sums[(size_t)c * d + t] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) counts[c] = 0;
+}
+
+__global__ void centroid_dist_kernel(const double* __restrict__ cen, int C, int d, double* __restrict__ cdist) {
+    const int a = blockIdx.x;
+    for (int b = threadIdx.x; b < C; b += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < d; ++t) { const double df = cen[(size_t)a * d + t] - cen[(size_t)b * d + t]; s = fma(df, df, s); }
+        cdist[(size_t)a * C + b] = sqrt(s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Assignment of every row, grouping
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restrict__ X, int64_t n, int d, int dp, int C,
+                                                       const double* __restrict__ cen, const double* __restrict__ cnorm,
+                                                       int32_t* __restrict__ cid, int* __restrict__ counts) {
+    extern __shared__ double rows[];
+    const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
+    stage_rows(X, row0, n, d, dp, rows);
+    __syncthreads();
+    const int64_t i = row0 + threadIdx.x;
+    const bool valid = i < n;
+    int c = -1;
+    if (valid) {
+        c = nearest_centroid(rows + threadIdx.x * dp, d, C, cen, cnorm);
+        cid[i] = c;
+    }
+    // warp-aggregated histogram
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + c, __popc(peers));
+}
+
+// tile0[c]: first reference tile of cluster c; slot0[c]: first query slot; cursors zeroed.
+__global__ void offsets_kernel(const int* __restrict__ cnt_ref, const int* __restrict__ cnt_q, int C, int* __restrict__ tile0,
+                               int* __restrict__ row_base, int* __restrict__ slot_base, int* __restrict__ nslots, int* __restrict__ cursors) {
+    if (threadIdx.x == 0) {
+        int t = 0, s = 0;
+        for (int c = 0; c < C; ++c) {
+            tile0[c] = t;
+            row_base[c] = t * CL_TILE;
+            slot_base[c] = s;
+            t += (cnt_ref[c] + CL_TILE - 1) / CL_TILE;
+            s += ((cnt_q[c] + CL_TILE - 1) / CL_TILE) * CL_TILE;
+        }
+        tile0[C] = t;
+        *nslots = s;
+    }
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) cursors[c] = 0;
+}
+
+__global__ void scatter_kernel(const int32_t* __restrict__ cid, int64_t n, const int* __restrict__ base, int* __restrict__ cursor,
+                               int32_t* __restrict__ map) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int c = valid ? cid[i] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    int start = 0;
+    if (valid && lane == leader) start = atomicAdd(cursor + c, __popc(peers));
+    start = __shfl_sync(0xffffffffu, start, leader);
+    if (valid) map[base[c] + start + __popc(peers & ((1u << lane) - 1u))] = (int32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Projections of a tile's rows on the centroid axes
+// ---------------------------------------------------------------------------------------------------------------
+// Block = 256 threads, 128 rows: thread (r = tid & 127, h = tid >> 7) handles the clusters [h*C/2, (h+1)*C/2) of row r.
+// MODE 0 (reference tile): vref[P][c] = max over rows of (x.c_c - x.c_P) / D(P,c) + margin   (P = the tile's cluster)
+// MODE 1 (query tile)    : LB[c] = min over rows of -ext_c(P_r) - (q.c_c - q.c_P_r) / D(P_r,c) - margin, then the sorted
+//                          cluster list and the per-slot score offsets.
+template <int MODE>
+__global__ void __launch_bounds__(256) tile_project_kernel(const double* __restrict__ X, int d, int dp, int C, const int32_t* __restrict__ map,
+                                                         const int* __restrict__ count, const int32_t* __restrict__ cid,
+                                                         const double* __restrict__ cen, const double* __restrict__ cdist,
+                                                         unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
+                                                         const double* __restrict__ qnorm, const int* __restrict__ scale_exp,
+                                                         int2* __restrict__ lists, float* __restrict__ qoff) {
+    extern __shared__ double rows[];                 // [128][dp]
+    __shared__ unsigned long long red[CL_MAXC];
+    __shared__ int src_s[CL_TILE];
+    const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
+    if (count && row0 >= (int64_t)*count) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < CL_TILE) src_s[tid] = (!count || row0 + tid < (int64_t)*count) ? map[row0 + tid] : -1;
+    for (int c = tid; c < CL_MAXC; c += 256) red[c] = (MODE == 0) ? dkey(-INFINITY) : dkey(INFINITY);
+    __syncthreads();
+    if (MODE == 0 && src_s[0] < 0) return;           // clusters are padded at their end: an empty first row = an unused tile
+    for (int r = warp; r < CL_TILE; r += 8) {
+        const int64_t s = src_s[r];
+        for (int t = lane; t < d; t += 32) rows[r * dp + t] = (s >= 0) ? X[s * d + t] : 0.0;
+    }
+    __syncthreads();
+    const int r = tid & 127, h = tid >> 7;
+    const int src = src_s[r];
+    const bool valid = src >= 0;
+    const int P = valid ? cid[src] : 0;
+    const double* x = rows + r * dp;
+    const double M = sqrt(__longlong_as_double((long long)*maxnorm_bits));
+    double gP = 0.0, xn = 0.0;
+    {
+        const double* cp = cen + (size_t)P * d;
+        for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, __ldg(cp + t), gP); xn = fma(xv, xv, xn); }
+    }
+    const double mg_num = 1e-11 * (sqrt(xn) + M) * M;   // >= 1000x the rounding error of the two dot products
+    const double tiny = 1e-5 * M;
+    const int cbeg = h * (C / 2), cend = cbeg + C / 2;
+    for (int c0 = cbeg; c0 < cend; c0 += 4) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* p0 = cen + (size_t)c0 * d;
+        for (int t = 0; t < d; ++t) {
+            const double xv = x[t];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = fma(xv, __ldg(p0 + (size_t)u * d + t), a[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = c0 + u;
+            const double D = cdist[(size_t)P * C + c];
+            double val;
+            if (MODE == 0) {
+                // extent of this row towards centroid c, rounded up; coincident centroids give no usable axis
+                val = (valid && c != P) ? ((D > tiny) ? (a[u] - gP) / D + mg_num / D : INFINITY) : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val = fmax(val, __shfl_xor_sync(0xffffffffu, val, o));
+                if (lane == 0) atomicMax(&red[c], dkey(val));
+            } else {
+                if (!valid) val = INFINITY;
+                else if (c == P || !(D > tiny)) val = -INFINITY;
+                else {
+                    const double ext = dkey_inv(vref[(size_t)c * C + P]);   // -inf for an empty cluster -> LB = +inf
+                    val = -ext - (a[u] - gP) / D - mg_num / D;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, o));
+                if (lane == 0) atomicMin(&red[c], dkey(val));
+            }
+        }
+    }
+    __syncthreads();
+    if (MODE == 0) {
+        const int Pt = cid[src_s[0]];
+        for (int c = tid; c < C; c += 256)
+            if (c != Pt) atomicMax(&vref[(size_t)Pt * C + c], red[c]);
+        return;
+    }
+    // MODE 1: keys (float bits of S^2 LB^2 rounded down, cluster), ascending
+    const double S2 = scalbn(1.0, 2 * (*scale_exp));
+    int CP = 1;
+    while (CP < C) CP <<= 1;
+    unsigned long long key = ~0ull;
+    if (tid < C) {
+        const double LB = dkey_inv(red[tid]);
+        float lb;
+        if (!(LB > 0.0)) lb = 0.f;
+        else if (isinf(LB)) lb = __int_as_float(0x7f800000);
+        else lb = __double2float_rd(S2 * LB * LB * (1.0 - 1e-6));
+        key = ((unsigned long long)__float_as_uint(lb) << 32) | (unsigned)tid;
+    }
+    __syncthreads();
+    if (tid < CP) red[tid] = key;
+    __syncthreads();
+    for (int k = 2; k <= CP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (tid < CP) {
+                const int partner = tid ^ j;
+                if (partner > tid) {
+                    const unsigned long long a0 = red[tid], b0 = red[partner];
+                    const bool up = (tid & k) == 0;
+                    if ((a0 > b0) == up) { red[tid] = b0; red[partner] = a0; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < C) {
+        const unsigned long long kk = red[tid];
+        lists[(size_t)blockIdx.x * C + tid] = make_int2((int)(unsigned)kk, (int)(unsigned)(kk >> 32));
+    }
+    if (tid < CL_TILE) {
+        const int s = src_s[tid];
+        qoff[row0 + tid] = (s >= 0) ? __double2float_ru(S2 * qnorm[s] * (1.0 + 1e-6)) : __int_as_float(0xff800000);
+    }
+}
+
+__global__ void fill_vref_kernel(unsigned long long* __restrict__ vref, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vref[i] = dkey(-INFINITY);
+}
+
+}  // namespace
+
+static int set_smem(const void* fn, size_t bytes) {
+    B200_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int C, const double* qnorm, const int* scale_exp,
+                       const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream, ClusterPlan* plan) {
+    if (C < 8 || C > CL_MAXC || (C & (C - 1)) != 0) return fail(B200MNN_EINVAL, "internal: cluster count must be a power of two in [8, 256]");
+    int m = (int)std::min<int64_t>(n, SAMPLE_MAX);
+    const int mf = std::min(m, FPS_MAX);
+    m = (m / mf) * mf;          // the seeding walks the sample with an integer stride
+    if (mf < C) return fail(B200MNN_EINVAL, "internal: too few rows for the requested number of clusters");
+    const int dp = d | 1;
+    const size_t row_smem = (size_t)CL_TILE * dp * sizeof(double);
+    if (row_smem > (size_t)200 * 1024) return fail(B200MNN_EINVAL, "internal: too many dimensions for the cluster plan");
+
+    ClusterPlan& p = *plan;
+    p.C = C;
+    p.n_rows_max = round_up(n, CL_TILE) + (int64_t)C * CL_TILE;
+    p.nslots_max = round_up(nq, CL_TILE) + (int64_t)C * CL_TILE;
+    p.refmap = ws.get<int32_t>((size_t)p.n_rows_max);
+    p.qmap = ws.get<int32_t>((size_t)p.nslots_max);
+    p.cl_list = ws.get<int2>((size_t)(p.nslots_max / CL_TILE) * C);
+    p.qoff = ws.get<float>((size_t)p.nslots_max);
+    p.cid_q = ws.get<int32_t>((size_t)nq);
+    p.centroids = ws.get<double>((size_t)C * d);
+    p.cdist = ws.get<double>((size_t)C * C);
+    p.vref = ws.get<unsigned long long>((size_t)C * C);
+    int32_t* cid_ref = ws.get<int32_t>((size_t)n);
+    double* sample = ws.get<double>((size_t)m * d);
+    double* sums = ws.get<double>((size_t)C * d);
+    double* cnorm = ws.get<double>((size_t)C);
+    int* ints = ws.get<int>((size_t)8 * CL_MAXC + 16);
+    if (!ws.ok()) return B200MNN_ENOMEM;
+    int* counts = ints;                    // [C]   Lloyd counts
+    int* cnt_ref = ints + CL_MAXC;         // [C]
+    int* cnt_q = ints + 2 * CL_MAXC;       // [C]
+    int* row_base = ints + 3 * CL_MAXC;    // [C]
+    int* slot_base = ints + 4 * CL_MAXC;   // [C]
+    int* cursors = ints + 5 * CL_MAXC;     // [2C]
+    p.cl_tile0 = ints + 7 * CL_MAXC;       // [C + 1]
+    p.nslots = ints + 8 * CL_MAXC + 8;
+    B200_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * (8 * CL_MAXC + 16), stream));
+    B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)C * d, stream));
+    B200_CUDA(cudaMemsetAsync(p.refmap, 0xFF, sizeof(int32_t) * (size_t)p.n_rows_max, stream));
+    B200_CUDA(cudaMemsetAsync(p.qmap, 0xFF, sizeof(int32_t) * (size_t)p.nslots_max, stream));
+
+    B200_TRY(set_smem((const void*)lloyd_accum_kernel, row_smem));
+    B200_TRY(set_smem((const void*)assign_kernel, row_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<0>, row_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<1>, row_smem));
+
+    gather_sample_kernel<<<(unsigned)ceil_div((int64_t)m * d, 256), 256, 0, stream>>>(dX, n, d, m, sample);
+    B200_LAUNCH_CHECK();
+    fps_seed_kernel<<<1, 1024, 0, stream>>>(sample, m, d, mf, C, p.centroids);
+    B200_LAUNCH_CHECK();
+    for (int it = 0; it < LLOYD_ITERS; ++it) {
+        centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
+        B200_LAUNCH_CHECK();
+        lloyd_accum_kernel<<<(unsigned)ceil_div(m, CL_TILE), CL_TILE, row_smem, stream>>>(sample, m, d, dp, C, p.centroids, cnorm, sums, counts);
+        B200_LAUNCH_CHECK();
+        lloyd_update_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, sums, counts);
+        B200_LAUNCH_CHECK();
+    }
+    centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
+    B200_LAUNCH_CHECK();
+    centroid_dist_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, p.cdist);
+    B200_LAUNCH_CHECK();
+
+    assign_kernel<<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, row_smem, stream>>>(dX, n, d, dp, C, p.centroids, cnorm, cid_ref, cnt_ref);
+    B200_LAUNCH_CHECK();
+    assign_kernel<<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, row_smem, stream>>>(dQ, nq, d, dp, C, p.centroids, cnorm, p.cid_q, cnt_q);
+    B200_LAUNCH_CHECK();
+    offsets_kernel<<<1, 256, 0, stream>>>(cnt_ref, cnt_q, C, p.cl_tile0, row_base, slot_base, p.nslots, cursors);
+    B200_LAUNCH_CHECK();
+    scatter_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cid_ref, n, row_base, cursors, p.refmap);
+    B200_LAUNCH_CHECK();
+    scatter_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, stream>>>(p.cid_q, nq, slot_base, cursors + C, p.qmap);
+    B200_LAUNCH_CHECK();
+
+    fill_vref_kernel<<<(unsigned)ceil_div((int64_t)C * C, 256), 256, 0, stream>>>(p.vref, C * C);
+    B200_LAUNCH_CHECK();
+    tile_project_kernel<0><<<(unsigned)(p.n_rows_max / CL_TILE), 256, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids,
+                                                                                        p.cdist, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
+    B200_LAUNCH_CHECK();
+    B200_TRY(build_tile_lists(p, dQ, d, p.qmap, p.nslots, p.nslots_max, qnorm, scale_exp, maxnorm_bits, p.cl_list, p.qoff, stream));
+    return 0;
+}
+
+int build_tile_lists(const ClusterPlan& p, const double* dQ, int d, const int32_t* qmap, const int* count, int64_t max_slots,
+                     const double* qnorm, const int* scale_exp, const unsigned long long* maxnorm_bits, int2* lists, float* qoff,
+                     cudaStream_t stream) {
+    const int dp = d | 1;
+    const size_t row_smem = (size_t)CL_TILE * dp * sizeof(double);
+    tile_project_kernel<1><<<(unsigned)(max_slots / CL_TILE), 256, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids, p.cdist,
+                                                                                     p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace knn
+}  // namespace b200

@@ -1,0 +1,44 @@
+// Cluster plan of the pruned exact kNN search (csrc/knn_cluster.cu): reference rows grouped by a coarse k-means,
+// query rows grouped by their nearest reference centroid, and -- per tile of 128 grouped queries -- the reference
+// clusters in ascending order of a rigorous lower bound on the query-to-cluster distance.  This is the B200 form of
+// what KMKNN does on the CPU (k-means + triangle-inequality pruning inside BiocNeighbors::queryKNN, the call at
+// R/MNN_tree.R:129): the search stays exact, whole 128x128 score tiles are skipped instead of single points.
+#pragma once
+
+#include "common.cuh"
+
+namespace b200 {
+namespace knn {
+
+constexpr int CL_MAXC = 256;     // clusters (power of two)
+constexpr int CL_TILE = 128;     // rows per tile: = TS_BN (reference tile) = BM (query tile)
+
+struct ClusterPlan {
+    int C = 0;
+    int64_t n_rows_max = 0;      // rows of the grouped + padded reference operand (multiple of CL_TILE, host-side upper bound)
+    int64_t nslots_max = 0;      // query slots (multiple of CL_TILE, host-side upper bound)
+    int32_t* refmap = nullptr;   // [n_rows_max]  grouped reference row -> original row (-1: padding)
+    int32_t* qmap = nullptr;     // [nslots_max]  query slot -> original query (-1: padding)
+    int* nslots = nullptr;       // device scalar: slots in use (multiple of CL_TILE)
+    int* cl_tile0 = nullptr;     // [C + 1] first reference tile of every cluster
+    int2* cl_list = nullptr;     // [nslots_max / CL_TILE][C]  (cluster, float bits of S^2 * lower_bound^2), ascending
+    float* qoff = nullptr;       // [nslots_max]  S^2 ||q||^2 rounded up (-inf for padding slots)
+    int32_t* cid_q = nullptr;    // [nq] cluster of every query (original order)
+    double* centroids = nullptr; // [C][d]
+    double* cdist = nullptr;     // [C][C] centroid distances
+    unsigned long long* vref = nullptr;   // [C][C] ordered-key maxima: extent of cluster B's rows towards centroid A
+};
+
+// Builds the plan on `stream` (no host synchronisation).  qnorm: fp64 squared norms of the queries (original order),
+// scale_exp / maxnorm_bits: the device scalars of the scoring pipeline (knn_tc.cu).
+int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int C, const double* qnorm, const int* scale_exp,
+                       const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream, ClusterPlan* plan);
+
+// Cluster lists (+ score offsets) for an arbitrary slot -> query map (used for the second scoring tier, whose slots are
+// the uncertified queries in slot order): count is a device scalar, lists/qoff are sized for max_slots.
+int build_tile_lists(const ClusterPlan& plan, const double* dQ, int d, const int32_t* qmap, const int* count, int64_t max_slots,
+                     const double* qnorm, const int* scale_exp, const unsigned long long* maxnorm_bits, int2* lists, float* qoff,
+                     cudaStream_t stream);
+
+}  // namespace knn
+}  // namespace b200

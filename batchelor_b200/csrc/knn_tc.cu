@@ -22,6 +22,7 @@
 //   K4 rescue         : flagged queries are recomputed by an exact fp64 scan of all references.  This is also
 //                       the generic path for shapes the tensor path does not cover (k > 56, d > 192).
 #include "common.cuh"
+#include "knn_cluster.cuh"
 
 #include <cuda.h>
 
@@ -854,6 +855,16 @@ constexpr int TS_PENDW = 24;                 // pending keys per row and epilogu
 // first tiles: scanned by one warp of each pair with a compaction after every chunk; afterwards a row sees on average
 // 64 * KEEP / (128 * boot tiles) = 8 hits per 64 columns, far below the 24 pending slots of a warp
 constexpr int TS_BOOT_TILES_PER_E = 2;
+constexpr int TS_RING = 32;                  // tile-id ring between the producer and its consumers (>= tiles in flight + 2)
+// Pruned search (knn_cluster.cuh): per query tile the reference clusters in ascending order of their lower bound.
+// cl_list == nullptr: dense scan of tiles [tile0, tile1).
+struct PruneArgs {
+    const int2* cl_list;     // [query tile][C] (cluster, float bits of S^2 LB^2)
+    const int* cl_tile0;     // [C + 1] first reference tile of every cluster
+    const float* qoff;       // [slot] S^2 ||q||^2 rounded up, -inf for padding slots
+    int C;
+    unsigned long long* visited;   // optional counter: tiles scored by this launch
+};
 template <int E>
 struct TsCand {
     static constexpr int KEEP = 32 * E;
@@ -961,7 +972,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                          float* __restrict__ thr_out,      // [nsplit][nq]
                          const int dbg_mode,               // measurement aid: 1 = stages recycled unread, 3 = no TMA, 4 = no MMAs
                          long long* __restrict__ dbg_ts,   // optional: per-warp cycle accounting of CTA (0,0)
-                         const int trace_start) {
+                         const int trace_start, const PruneArgs P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0u) __trap();
     const int64_t nq_eff = qcount ? (int64_t)*qcount : nq;   // rows that exist; nq stays the stride of the output arrays
@@ -978,7 +989,9 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     float* thr_s = reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                                // [128]
     int* dirty_s = reinterpret_cast<int*>(thr_s + BM);                                                         // [128]
     int* locks = dirty_s + BM;                                                                                 // [4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(locks + 4);
+    volatile int* ring = locks + 4;                                                                            // [TS_RING] tile ids, -1 = end
+    float* qoff_s = reinterpret_cast<float*>(locks + 4 + TS_RING);                                             // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + BM);
     uint64_t* full = bars;                     // [MAX_SLOTS]
     uint64_t* empty = bars + MAX_SLOTS;        // [MAX_SLOTS]
     uint64_t* aready = bars + 2 * MAX_SLOTS;   // [1] query operand is in TMEM (4 warp arrivals)
@@ -988,7 +1001,6 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
 
     const int tile0 = blockIdx.y * tiles_per_split;
     const int tile1 = min(ntiles, tile0 + tiles_per_split);
-    const int my_tiles = tile1 - tile0;
     const int m0 = blockIdx.x * BM;
 #ifdef B200_TRACE   // per-warp cycle accounting of CTA (0,0): compiled in only for measurement builds (tools/build_variant.sh)
     const bool trace = dbg_ts != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -1011,7 +1023,11 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         for (int i = 0; i < TS_STAGES; ++i) { mbar_init(smem_u32(&tfull[i]), 1); mbar_init(smem_u32(&tempty[i]), TS_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (threadIdx.x < BM) { thr_s[threadIdx.x] = __int_as_float(0x7f800000); dirty_s[threadIdx.x] = 0; }
+    if (threadIdx.x < BM) {
+        thr_s[threadIdx.x] = __int_as_float(0x7f800000);
+        dirty_s[threadIdx.x] = 0;
+        qoff_s[threadIdx.x] = (P.cl_list && (int64_t)m0 + threadIdx.x < nq_eff) ? P.qoff[m0 + threadIdx.x] : __int_as_float(0xff800000);
+    }
     if (threadIdx.x < 4) locks[threadIdx.x] = 0;
     if (warp == 1) {
         tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -1025,23 +1041,62 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int t = tile0; t < tile1; ++t) {
+        // The producer decides which tiles are scored and tells its consumers through the tile-id ring: entry seq % TS_RING
+        // is written before the tile's first box is armed (the mbarrier arrive releases it), -1 ends the stream.  Every
+        // entry -- the two end markers (one per MMA issuer) included -- occupies NBOX slots of the box ring.
+        int slot = 0;
+        uint32_t phase = 0;
+        int seq = 0;
+        auto emit = [&](const int tile) {
+            if (lane == 0) {
+                ring[seq & (TS_RING - 1)] = tile;
 #pragma unroll
                 for (int b = 0; b < NBOX; ++b) {
                     mbar_wait(smem_u32(&empty[slot]), phase ^ 1);   // lane 0 only
-                    if (dbg_mode == 3) {
+                    if (tile < 0 || dbg_mode == 3) {
                         mbar_arrive(smem_u32(&full[slot]));
                     } else {
                         mbar_arrive_expect_tx(smem_u32(&full[slot]), (uint32_t)TS_B_BOX_BYTES);
-                        tma_load_2d(smem_u32(smB + (size_t)slot * TS_B_BOX_BYTES), &tmB, smem_u32(&full[slot]), b * KBOX, t * TS_BN);
+                        tma_load_2d(smem_u32(smB + (size_t)slot * TS_B_BOX_BYTES), &tmB, smem_u32(&full[slot]), b * KBOX, tile * TS_BN);
                     }
                     if (++slot == nslot) { slot = 0; phase ^= 1; }
                 }
             }
+            ++seq;
+            __syncwarp();
+        };
+        if (P.cl_list) {
+            // Pruned search: clusters in ascending order of their lower bound; the stream ends at the first cluster whose
+            // bound S^2 LB^2 is no smaller than S^2 d^2 of the threshold of EVERY row (thresholds only decrease, so a stale
+            // read is merely lenient).  Unseen references then satisfy score >= threshold like every rejected one.
+            const int2* list = P.cl_list + (size_t)blockIdx.x * P.C;
+            const volatile float* thr_v = thr_s;
+            bool stop = false;
+            for (int ci = 0; ci < P.C && !stop; ++ci) {
+                const int2 e = list[ci];
+                const float lb = __int_as_float(e.y);
+                const int t0 = P.cl_tile0[e.x], t1 = P.cl_tile0[e.x + 1];
+                for (int t = t0; t < t1; ++t) {
+                    if (lb > 0.f) {
+                        float m = __int_as_float(0xff800000);
+#pragma unroll
+                        for (int r = lane; r < BM; r += 32) {
+                            const float qo = qoff_s[r];
+                            if (qo > __int_as_float(0xff800000)) m = fmaxf(m, __fadd_ru(thr_v[r], qo));
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        if (lb >= m) { stop = true; break; }
+                    }
+                    emit(t);
+                }
+            }
+        } else {
+            for (int t = tile0; t < tile1; ++t) emit(t);
         }
+        if (P.visited && lane == 0) atomicAdd(P.visited, (unsigned long long)seq);
+        emit(-1);
+        emit(-1);
     } else if (warp == 1 || warp == 10) {
         // ===================== MMA issuers (even / odd tiles) =====================
         uint32_t aT[NBOX][MAX_MMA_PER_BOX];   // TMEM address of the A slice of every scheduled MMA
@@ -1060,7 +1115,8 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         mbar_wait_u(smem_u32(aready), 0);
         tc_fence_after();
         const int mma_id = (warp == 1) ? 0 : 1;
-        for (int tl = mma_id; tl < my_tiles; tl += 2) {
+        bool more = true;
+        for (int tl = mma_id; more; tl += 2) {
             const int stage = tl % TS_STAGES;
             const uint32_t use = (uint32_t)(tl / TS_STAGES);
             mbar_wait_u(smem_u32(&tempty[stage]), (use & 1) ^ 1);
@@ -1073,11 +1129,17 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             for (int b = 0; b < NBOX; ++b) {
                 mbar_wait_u(smem_u32(&full[slot]), phase);
                 tc_fence_after();
+                if (b == 0 && ring[tl & (TS_RING - 1)] < 0) {   // end marker: pass it on to the epilogue, done
+                    if (elect_one()) mbar_arrive(smem_u32(&tfull[stage]));
+                    __syncwarp();
+                    more = false;
+                    break;
+                }
                 const uint64_t db0 = db_base + (uint64_t)((uint32_t)slot * (uint32_t)(TS_B_BOX_BYTES >> 4));
                 if (elect_one()) {
                     if (dbg_mode != 4) {
-#pragma unroll
                         const int nmb = (dbg_mode == 6) ? min(nm[b], 2) : nm[b];   // 6: measurement aid, fewer MMAs per tile
+#pragma unroll
                         for (int m = 0; m < MAX_MMA_PER_BOX; ++m)
                             if (m < nmb) umma_f16_ts_impl(tmem_d, aT[b][m], db0 + oB[b][m], idesc, (b == 0 && m == 0) ? 0u : 1u);
                     }
@@ -1105,7 +1167,12 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         int stat[3] = {0, 0, 0};
         long long mstat[6] = {0, 0, 0, 0, 1LL << 60, 0};   // lock wait cycles, merge calls, merged rows, row cycles sum/min/max
         uint32_t v0[32], v1[32];
-        const int nboot = min(my_tiles, TS_BOOT_TILES_PER_E * E);
+        constexpr int NBOOT = TS_BOOT_TILES_PER_E * E;
+        // Tiles arrive in the producer's order; entry seq of the tile-id ring names the tile in accumulator stage
+        // seq % TS_STAGES (-1: end of the stream; both warps of a pair see it at the same seq).
+        int seq = 0, stage = 0;
+        uint32_t par = 0;
+        bool ended = false;
 
         if (grp == 0) {
             // (1) this thread's query row -> TMEM (A operand of every MMA of this CTA)
@@ -1127,11 +1194,12 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             int cnt = 0;
             bool sorted = false;
             float thr = __int_as_float(0x7f800000);
-            for (int tl = 0; tl < nboot; ++tl) {
-                const int stage = tl % TS_STAGES;
-                mbar_wait_u(smem_u32(&tfull[stage]), (uint32_t)((tl / TS_STAGES) & 1));
+            for (int tb = 0; tb < NBOOT; ++tb) {
+                mbar_wait_u(smem_u32(&tfull[stage]), par);
                 tc_fence_after();
-                const int colbase = (tile0 + tl) * TS_BN;
+                const int tile = ring[seq & (TS_RING - 1)];
+                if (tile < 0) { ended = true; break; }
+                const int colbase = tile * TS_BN;
                 const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
 #pragma unroll 1
                 for (int c = 0; c < TS_BN / 32; ++c) {
@@ -1147,14 +1215,18 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                         if (__any_sync(0xffffffffu, cnt > KEEP)) compact_rows<E>(mybuf, lane, KEEP, thr, cnt, sorted);
                     }
                 }
+                ++seq;
+                if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
             }
             compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);   // every row sorted (padded with EMPTY_KEY), thresholds final
             thr_row[lane] = (dbg_mode == 8) ? __int_as_float(0xff800000) : thr;   // 8: measurement aid, no hit ever
         } else {
-            for (int tl = 0; tl < nboot; ++tl) {
-                const int stage = tl % TS_STAGES;
-                mbar_wait_u(smem_u32(&tfull[stage]), (uint32_t)((tl / TS_STAGES) & 1));
+            for (int tb = 0; tb < NBOOT; ++tb) {
+                mbar_wait_u(smem_u32(&tfull[stage]), par);
+                if (ring[seq & (TS_RING - 1)] < 0) { ended = true; break; }
                 if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                ++seq;
+                if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
             }
         }
         pair_fence();
@@ -1168,15 +1240,16 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         // chain: wait, two TMEM loads, release, min tree, ONE vote.  Stage/parity are carried in registers, the row
         // threshold is re-read from shared memory only after a hit (own merge) or every 8th tile (partner's merges: a
         // stale threshold is merely lenient), and the pending counts are only inspected after a hit.
-        int stage = nboot % TS_STAGES;
-        uint32_t par = (uint32_t)((nboot / TS_STAGES) & 1);
         const bool skip_read = dbg_mode == 1;
         float thr = thr_row[lane];
-        for (int tl = nboot; tl < my_tiles; ++tl) {
+        int steady = 0;
+        while (!ended) {
             long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             if (trace) c0 = clock64();
             mbar_wait_u(smem_u32(&tfull[stage]), par);
             tc_fence_after();
+            const int tile = ring[seq & (TS_RING - 1)];
+            if (tile < 0) break;
             if (trace) c1 = clock64();
             if (!skip_read) {
                 const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN + grp * 64);
@@ -1188,23 +1261,28 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
             if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
+            ++seq;
+            ++steady;
             if (trace) c2 = clock64();
             if (skip_read) continue;
-            const bool hit = scan_pair<TS_PENDW>(v0, v1, (tile0 + tl) * TS_BN + grp * 64, thr, pc, dirty, pend, stg, lane, trace ? stat : nullptr);
+            const bool hit = scan_pair<TS_PENDW>(v0, v1, tile * TS_BN + grp * 64, thr, pc, dirty, pend, stg, lane, trace ? stat : nullptr);
             if (trace) c3 = clock64();
-            const bool last = tl == my_tiles - 1;
-            if (hit || last) {   // warp-uniform
+            if (hit) {   // warp-uniform
                 // early tiles still see several hits per row and pair of chunks: start every pair with an empty segment
-                const int limit = (last || tl < 32) ? 0 : TS_PENDW / 2;
+                const int limit = (seq < 32) ? 0 : TS_PENDW / 2;
                 const unsigned todo = __ballot_sync(0xffffffffu, pc > limit);
                 if (todo) compact_pending<E>(mybuf, pbase, lane, todo, pc, thr_row, lock, trace ? mstat : nullptr);
                 thr = thr_row[lane];
-            } else if ((tl & 7) == 0) {
+            } else if ((seq & 7) == 0) {
                 thr = thr_row[lane];
             }
             if (trace) {
                 acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; acc_t[2] += c3 - c2; acc_t[3] += clock64() - c3;
             }
+        }
+        {   // end of the stream: merge what is still pending
+            const unsigned todo = __ballot_sync(0xffffffffu, pc > 0);
+            if (todo) compact_pending<E>(mybuf, pbase, lane, todo, pc, thr_row, lock, trace ? mstat : nullptr);
         }
         if (dirty) dirty_row[lane] = 1;
         pair_fence();
@@ -1212,7 +1290,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         if (trace && lane == 0) {
             for (int i = 0; i < 4; ++i) dbg_ts[(warp - 2) * 8 + i] = acc_t[i];
             for (int i = 0; i < 3; ++i) dbg_ts[(warp - 2) * 8 + 4 + i] = stat[i];
-            dbg_ts[(warp - 2) * 8 + 7] = my_tiles - nboot;
+            dbg_ts[(warp - 2) * 8 + 7] = steady;
             for (int i = 0; i < 6; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = mstat[i];
         }
         // (4) output: the two warps of a pair write 16 rows each
@@ -1312,15 +1390,17 @@ template <bool IS_QUERY>
 __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int64_t n_pad, int d, KLayout L,
                                     const int* __restrict__ scale_exp, __half* __restrict__ op, const double* __restrict__ norm_f64,
                                     float2* __restrict__ qerr,            // queries: (|a - ah|, |ah|) over the full-group dims, rounded up
-                                    unsigned int* __restrict__ bmax_bits  // references: max |bh| and max |b - bh| (float bits, rounded up)
+                                    unsigned int* __restrict__ bmax_bits, // references: max |bh| and max |b - bh| (float bits, rounded up)
+                                    const int32_t* __restrict__ rowmap    // optional: operand row i holds X[rowmap[i]] (-1: padding), i < n_pad
                                     ) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
+    const int64_t srow = rowmap ? (int64_t)rowmap[i] : (i < n ? i : -1);
     const int KS = L.nbox * KBOX;
     uint4* row = reinterpret_cast<uint4*>(op + i * KS);
     __align__(16) __half hbuf[16];
     __align__(16) __half lbuf[16];
-    if (i >= n) {
+    if (srow < 0) {
         // padding: zero operand; a padded REFERENCE row gets an infinite norm so that it never becomes a candidate
         for (int c = 0; c < KS / 8; ++c) row[c] = make_uint4(0, 0, 0, 0);
         if (!IS_QUERY) {
@@ -1335,7 +1415,7 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
     }
     const double S = scalbn(1.0, *scale_exp);
     const double mul = IS_QUERY ? -2.0 * S : S;
-    const double* x = X + i * d;
+    const double* x = X + srow * d;
     double hi2 = 0.0, lo2 = 0.0;   // squared norms of the hi parts and of the exact residuals (what the one-term schedule drops)
     for (int g = 0; g < L.groups; ++g) {
 #pragma unroll
@@ -1358,7 +1438,7 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
     {
         const float fh = __double2float_ru(sqrt(hi2) * 1.0000001), fl = __double2float_ru(sqrt(lo2) * 1.0000001);
         if (IS_QUERY) {
-            if (qerr) qerr[i] = make_float2(fl, fh);
+            if (qerr) qerr[srow] = make_float2(fl, fh);
         } else if (bmax_bits) {   // non-negative floats order like their bit patterns
             atomicMax(bmax_bits + 0, __float_as_uint(fh));
             atomicMax(bmax_bits + 1, __float_as_uint(fl));
@@ -1371,7 +1451,7 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
         nc[1] = __float2half(16.f);         // 2^4
         nc[2] = __float2half(0.0078125f);   // 2^-7
     } else {
-        const double N = norm_f64[i] * S * S;
+        const double N = norm_f64[srow] * S * S;
         nc[0] = __double2half(N * 0.000030517578125);                           // N / 2^15
         const double r1 = N - (double)__half2float(nc[0]) * 32768.0;
         nc[1] = __double2half(r1 * 0.0625);                                     // r1 / 2^4
@@ -1426,12 +1506,14 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
               double* __restrict__ dbg_d2 /* [nq][ncand] or null */,
               const int32_t* __restrict__ qmap, const int* __restrict__ qcount,   // optional: list slot j holds query qmap[j], j < *qcount
               const int fast /* candidates came from the one-term schedule: wider error bound */,
-              const float2* __restrict__ qerr, const unsigned int* __restrict__ bmax_bits) {
+              const float2* __restrict__ qerr, const unsigned int* __restrict__ bmax_bits,
+              const int32_t* __restrict__ refmap /* optional: candidate ids are rows of the grouped operand -> original rows */) {
     __shared__ double stage[RR_WARPS][32][RR_DCH + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t jq = (int64_t)blockIdx.x * RR_WARPS + warp;   // slot in the candidate / threshold arrays
     if (jq >= (qcount ? (int64_t)*qcount : nq)) return;
     const int64_t q = qmap ? (int64_t)qmap[jq] : jq;            // the query itself
+    if (q < 0) return;                                          // padding slot of the grouped query order
     const int ncand = nsplit * ncand_per_split;
     const int rounds = ncand / 32;
     double cd[RR_MAXROUNDS];
@@ -1445,7 +1527,8 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
         if (r < rounds) {
             const int c = r * 32 + lane;
             const int sp = c / ncand_per_split, within = c % ncand_per_split;
-            const int id = cand_idx[((int64_t)sp * nq + jq) * ncand_per_split + within];
+            int id = cand_idx[((int64_t)sp * nq + jq) * ncand_per_split + within];
+            if (refmap && id >= 0) id = refmap[id];
             ci[r] = id;
             double acc = 0.0;
             for (int t0 = 0; t0 < d; t0 += RR_DCH) {
@@ -1584,11 +1667,16 @@ rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict_
 }
 
 __global__ void write_stats_kernel(const int* __restrict__ flag_count, int64_t* __restrict__ stats, int64_t lists, int64_t path,
-                                   const int* __restrict__ tier2_count = nullptr) {
+                                   const int* __restrict__ tier2_count = nullptr, const unsigned long long* __restrict__ visited = nullptr,
+                                   int64_t dense_tiles = 0) {
     stats[0] = flag_count ? *flag_count : 0;      // queries answered by the exact rescue kernel
     stats[1] = lists;
-    stats[2] = path;                              // 1: tensor path
+    stats[2] = path;                              // 1: tensor path, 2: tensor path with cluster pruning
     stats[3] = tier2_count ? *tier2_count : 0;    // queries the one-term tier could not certify (re-scored with three terms)
+    stats[4] = visited ? (int64_t)visited[0] : 0; // 128x128 score tiles computed by the first tier ...
+    stats[5] = visited ? (int64_t)visited[1] : 0; // ... and by the second
+    stats[6] = dense_tiles;                       // tiles of a dense scan of the same problem
+    stats[7] = 0;
 }
 
 // squared distance debug view: cand score -> unscaled approximate squared distance
@@ -1654,7 +1742,8 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 
 static size_t ts_smem_bytes(int nslot, int E) {
     return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + (size_t)(4 * (32 * E + 2 * TS_PENDW) * ROWPITCH + 2) * 8 +
-           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)BM * 8 + 16 + (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
+           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)BM * 8 + 16 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
+           (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
 }
 // TS variant: the operand must fit the TMEM columns next to the accumulators and at least nbox+1 reference boxes must
 // fit in shared memory next to the candidate rows.
@@ -1745,11 +1834,24 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     const bool ss_fits = candidates_smem_bytes(L.nbox, 3, E) <= (size_t)232448;
     const bool use_ts = ts_variant_fits(L.nbox, E) && !(ss_fits && kenv && strcmp(kenv, "ss") == 0);
     const int bn = use_ts ? TS_BN : BN;
-    const int64_t n_pad = round_up(n, bn), nq_pad = round_up(nq, BM);
+    // Pruned search (knn_cluster.cuh): reference rows grouped by a coarse k-means, query rows grouped by nearest centroid,
+    // whole clusters skipped by a rigorous lower bound.  B200MNN_PRUNE=0 never, =1 whenever the shape allows, unset: for
+    // searches large enough to pay for the clustering.  B200MNN_CLUSTERS sets the number of clusters (power of two).
+    int nclusters = 64;
+    if (const char* ce = getenv("B200MNN_CLUSTERS")) {
+        const int c = atoi(ce);
+        if (c >= 8 && c <= CL_MAXC && (c & (c - 1)) == 0) nclusters = c;
+    }
+    const char* penv = getenv("B200MNN_PRUNE");
+    const bool prune_ok = use_ts && !dbg && n >= 8 * (int64_t)nclusters && (size_t)CL_TILE * (d | 1) * sizeof(double) <= (size_t)200 * 1024;
+    const bool use_prune = prune_ok && (penv ? atoi(penv) == 1 : (n >= 65536 && nq >= 16384));
+    const int64_t n_pad = use_prune ? round_up(n, CL_TILE) + (int64_t)nclusters * CL_TILE : round_up(n, bn);
+    const int64_t nq_pad = round_up(nq, BM);
+    const int64_t nslots = use_prune ? round_up(nq, CL_TILE) + (int64_t)nclusters * CL_TILE : nq;   // rows of the candidate / threshold arrays
     const int ntiles = (int)(n_pad / bn);
-    const int mtiles = (int)(nq_pad / BM);
+    const int mtiles = use_prune ? (int)(nslots / BM) : (int)(nq_pad / BM);
     int nsplit = 1;
-    if (mtiles < 2 * sm_count()) nsplit = (int)std::min<int64_t>(std::min<int64_t>(MAX_SPLIT, ntiles), ceil_div(2 * sm_count(), mtiles));
+    if (!use_prune && mtiles < 2 * sm_count()) nsplit = (int)std::min<int64_t>(std::min<int64_t>(MAX_SPLIT, ntiles), ceil_div(2 * sm_count(), mtiles));
     const int tiles_per_split = (int)ceil_div(ntiles, nsplit);
     nsplit = (int)ceil_div(ntiles, tiles_per_split);
 
@@ -1757,13 +1859,14 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     __half* opA = ws.get<__half>((size_t)nq_pad * KS);
     double* xnorm = ws.get<double>((size_t)n_pad);
     double* qnorm = ws.get<double>((size_t)nq_pad);
-    int32_t* cand_idx = ws.get<int32_t>((size_t)nsplit * nq * per);
-    float* cand_score = dbg ? ws.get<float>((size_t)nsplit * nq * per) : nullptr;
-    float* thr = ws.get<float>((size_t)nsplit * nq);
+    int32_t* cand_idx = ws.get<int32_t>((size_t)nsplit * nslots * per);
+    float* cand_score = dbg ? ws.get<float>((size_t)nsplit * nslots * per) : nullptr;
+    float* thr = ws.get<float>((size_t)nsplit * nslots);
     int32_t* flag_list = ws.get<int32_t>((size_t)nq);
     int32_t* flag_list2 = ws.get<int32_t>((size_t)nq);
     float2* qerr = ws.get<float2>((size_t)nq_pad);
     unsigned char* scalars = ws.get<unsigned char>(64);
+    unsigned long long* visited = ws.get<unsigned long long>(2);
     if (!ws.ok()) return B200MNN_ENOMEM;
     unsigned int* absmax_bits = reinterpret_cast<unsigned int*>(scalars);
     int* scale_exp = reinterpret_cast<int*>(scalars + 8);
@@ -1772,6 +1875,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     int* flag_count2 = reinterpret_cast<int*>(scalars + 28);
     unsigned int* bmax_bits = reinterpret_cast<unsigned int*>(scalars + 32);   // [2]
     B200_CUDA(cudaMemsetAsync(scalars, 0, 64, stream));
+    B200_CUDA(cudaMemsetAsync(visited, 0, 16, stream));
 
     rowstat_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(dX, n, d, xnorm, absmax_bits, maxnorm_bits);
     B200_LAUNCH_CHECK();
@@ -1779,9 +1883,19 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     B200_LAUNCH_CHECK();
     scale_kernel<<<1, 1, 0, stream>>>(absmax_bits, maxnorm_bits, scale_exp);
     B200_LAUNCH_CHECK();
-    prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm, nullptr, bmax_bits);
+    ClusterPlan plan;
+    int2* lists2 = nullptr;
+    float* qoff2 = nullptr;
+    if (use_prune) {
+        B200_TRY(build_cluster_plan(dX, n, dQ, nq, d, nclusters, qnorm, scale_exp, maxnorm_bits, ws, stream, &plan));
+        lists2 = ws.get<int2>((size_t)(nslots / CL_TILE) * nclusters);
+        qoff2 = ws.get<float>((size_t)nslots);
+        if (!ws.ok()) return B200MNN_ENOMEM;
+    }
+    prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm, nullptr, bmax_bits,
+                                                                                  use_prune ? plan.refmap : nullptr);
     B200_LAUNCH_CHECK();
-    prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr, qerr, nullptr);
+    prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr, qerr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
 
     // Thread-block clusters (optional, B200MNN_CLUSTER=2|4): the CTAs of a cluster work on different query tiles against
@@ -1819,7 +1933,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     // worthwhile while k leaves a third of the kept candidates as margin.
     const bool two_tier = use_ts && !dbg && L.groups > 0 && 3 * k <= 2 * per && !(tenv && atoi(tenv) == 1);
 
-    auto launch_candidates = [&](bool fast, const int32_t* qmap, const int* qcount) -> int {
+    auto launch_candidates = [&](bool fast, const int32_t* qmap, const int* qcount, const PruneArgs& pargs, bool count_flops) -> int {
         const MmaSched sch = make_sched(L, fast);
         const int nb = fast ? L.nbox_fast : L.nbox;
         int nslot = MAX_SLOTS;
@@ -1854,7 +1968,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const int64_t nq_c = nq;
+        const int64_t nq_c = nslots;
         const __half* opA_c = opA;
         const int a_pitch = KS;
 #define B200_LAUNCH_CAND(EE, NB)                                                                                              \
@@ -1872,7 +1986,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     do {                                                                                                                          \
         B200_CUDA(cudaFuncSetAttribute(knn_candidates_ts_kernel<EE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_ts_kernel<EE, NB>, opA_c, a_pitch, qmap, qcount, tmB, sch, nslot, nq_c,  \
-                                     ntiles, tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start));         \
+                                     ntiles, tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start, pargs));  \
     } while (0)
 #define B200_LAUNCH_TS_E(NB)               \
     do {                                   \
@@ -1905,7 +2019,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
             B200_CUDA(cudaEventRecord(ev1, stream));
             std::lock_guard<std::mutex> lock(g_prof_mu);
             g_prof_events.emplace_back(ev0, ev1);
-            if (!qmap) g_prof_flops += 2.0 * (double)nq * (double)n * (double)d;   // algorithmic flops of the call, counted once
+            if (count_flops) g_prof_flops += 2.0 * (double)nq * (double)n * (double)d;   // algorithmic flops of the call, counted once
         }
         if (dbg_ts) {
             static long long h[64 * 32 + 64];
@@ -1944,7 +2058,16 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     };
 
     const bool fast_only_env = tenv && atoi(tenv) == 3;   // measurement aid: tier 1 only (uncertified queries go straight to the rescue)
-    B200_TRY(launch_candidates(two_tier, nullptr, nullptr));
+    PruneArgs prune1 = {nullptr, nullptr, nullptr, 0, visited};
+    PruneArgs prune2 = {nullptr, nullptr, nullptr, 0, visited + 1};
+    if (use_prune) {
+        prune1 = PruneArgs{plan.cl_list, plan.cl_tile0, plan.qoff, plan.C, visited};
+        prune2 = PruneArgs{lists2, plan.cl_tile0, qoff2, plan.C, visited + 1};
+    }
+    const int32_t* qmap1 = use_prune ? plan.qmap : nullptr;
+    const int* qcount1 = use_prune ? plan.nslots : nullptr;
+    const int32_t* refmap = use_prune ? plan.refmap : nullptr;
+    B200_TRY(launch_candidates(two_tier, qmap1, qcount1, prune1, true));
 
     if (dbg) {
         const int64_t ncand = (int64_t)nsplit * per;
@@ -1962,17 +2085,19 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         B200_CUDA(cudaMemsetAsync(d_dist, 0, sizeof(double) * (size_t)nq * k, stream));
         return 0;
     }
-    const unsigned rr_grid = (unsigned)ceil_div(nq, RR_WARPS);
-    rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nq, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
-                                                         d_dist, flag_count, flag_list, nullptr, nullptr, nullptr, two_tier ? 1 : 0, qerr, bmax_bits);
+    const unsigned rr_grid = (unsigned)ceil_div(nslots, RR_WARPS);
+    rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
+                                                         d_dist, flag_count, flag_list, nullptr, qmap1, qcount1, two_tier ? 1 : 0, qerr, bmax_bits, refmap);
     B200_LAUNCH_CHECK();
     const int* rescue_count = flag_count;
     const int32_t* rescue_list = flag_list;
     if (two_tier && !fast_only_env) {
         // tier 2: the flagged queries again, three-term schedule, same grid (CTAs past the flag count exit immediately)
-        B200_TRY(launch_candidates(false, flag_list, flag_count));
-        rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nq, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
-                                                             d_dist, flag_count2, flag_list2, nullptr, flag_list, flag_count, 0, qerr, bmax_bits);
+        if (use_prune)
+            B200_TRY(build_tile_lists(plan, dQ, d, flag_list, flag_count, nslots, qnorm, scale_exp, maxnorm_bits, lists2, qoff2, stream));
+        B200_TRY(launch_candidates(false, flag_list, flag_count, prune2, false));
+        rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
+                                                             d_dist, flag_count2, flag_list2, nullptr, flag_list, flag_count, 0, qerr, bmax_bits, refmap);
         B200_LAUNCH_CHECK();
         rescue_count = flag_count2;
         rescue_list = flag_list2;
@@ -1980,7 +2105,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     rescue_kernel<<<sm_count() * 4, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, k, rescue_count, rescue_list, nq, d_idx, d_dist);
     B200_LAUNCH_CHECK();
     if (d_stats) {
-        write_stats_kernel<<<1, 1, 0, stream>>>(rescue_count, d_stats, nsplit, 1, two_tier ? flag_count : nullptr);
+        write_stats_kernel<<<1, 1, 0, stream>>>(rescue_count, d_stats, nsplit, use_prune ? 2 : 1, two_tier ? flag_count : nullptr, use_ts ? visited : nullptr,
+                                                ceil_div(nq, BM) * ceil_div(n, TS_BN));
         B200_LAUNCH_CHECK();
     }
     return 0;

@@ -118,9 +118,11 @@ int b200mnn_tricube_weighted_correction(const double* curdata, int64_t n, int d,
  * ------------------------------------------------------------------------------------------------------------ */
 
 /* Exact kNN.  d_idx [nq x k] int32 0-based row-major; d_dist [nq x k] double or NULL.  Asynchronous on `stream`.
- * Path: fp16x3 tcgen05 candidate scoring -> exact fp64 re-rank + certificate -> exact fp64 rescue of any
- * uncertified query.  `d_stats` (may be NULL) receives int64[4]: {queries rescued, candidate lists per query,
- * path (1 = tensor, 0 = generic), reserved}. */
+ * Path: (large searches) k-means grouping of both sides + rigorous per-cluster lower bounds, then fp16 tcgen05 candidate
+ * scoring of the clusters that cannot be excluded -> exact fp64 re-rank + certificate -> three-term re-score and finally
+ * an exact fp64 rescue of any uncertified query.  `d_stats` (may be NULL) receives int64[8]: {queries rescued,
+ * candidate lists per query, path (2 = tensor + cluster pruning, 1 = tensor, 0 = generic), queries re-scored by the
+ * second tier, 128x128 score tiles computed by tier 1, by tier 2, tiles of a dense scan, reserved}. */
 int b200mnn_dev_query_knn(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k,
                           int32_t* d_idx, double* d_dist, int64_t* d_stats, void* stream);
 

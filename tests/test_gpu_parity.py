@@ -99,6 +99,73 @@ def test_query_knn_medium_against_kmknn_port():
     assert np.array_equal(got["distance"], dist)
 
 
+# Pruned search (csrc/knn_cluster.cu): forced on small inputs with few clusters; the answer must not change at all.
+@pytest.mark.parametrize("n,nq,d,k,ncomp,nclus", [
+    (6000, 5000, 50, 20, 8, 16),
+    (4097, 129, 50, 1, 8, 8),        # ragged tiles, k = 1
+    (3000, 3000, 50, 30, 8, 16),     # 64-entry candidate lists
+    (5000, 2000, 17, 7, 4, 32),      # more clusters than mixture components
+    (3000, 1000, 100, 10, 8, 8),
+    (2500, 4000, 3, 5, 2, 64),       # low dimension: bounds bite inside components too
+    (700, 300, 50, 20, 8, 8),        # barely enough rows for the clustering
+])
+def test_query_knn_pruned_matches_oracle_bit_exact(n, nq, d, k, ncomp, nclus, monkeypatch):
+    monkeypatch.setenv("B200MNN_PRUNE", "1")
+    monkeypatch.setenv("B200MNN_CLUSTERS", str(nclus))
+    X, Q = synth.pc_batches(2, [n, nq], d=d, ncomp=ncomp)
+    got = bb.queryKNN(X, Q, k)
+    idx, dist = capi.query_knn(X, Q, k)
+    assert np.array_equal(got["index"], idx), f"{int((got['index'] != idx).sum())} mismatching neighbour slots"
+    assert np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_pruned_degenerate_inputs(monkeypatch):
+    """Duplicates (coincident centroids), exact ties, unclustered data and far-apart blobs with the pruning forced on."""
+    monkeypatch.setenv("B200MNN_PRUNE", "1")
+    monkeypatch.setenv("B200MNN_CLUSTERS", "8")
+    rng = np.random.default_rng(11)
+    cases = []
+    X = np.zeros((600, 50)); X[:, 0] = np.repeat(np.arange(12.0), 50)          # 50 exact duplicates per location
+    cases.append((X, X[::7] + 0.0, 20))
+    cases.append((np.ones((400, 7)), np.ones((150, 7)), 9))                     # every point identical
+    cases.append((rng.normal(size=(3000, 50)), rng.normal(size=(1000, 50)), 20))  # one blob: nothing can be skipped
+    far = np.concatenate([rng.normal(size=(1500, 10)), rng.normal(size=(1500, 10)) + 1e3])
+    cases.append((far, np.concatenate([far[::5] + 0.25, rng.normal(size=(100, 10)) + 500.0]), 20))   # queries between blobs
+    cases.append((rng.normal(size=(2000, 50)) * 7.3 + 100.0, rng.normal(size=(700, 50)) * 7.3 + 100.0, 20))
+    for X, Q, k in cases:
+        got = bb.queryKNN(X, Q, k)
+        idx, dist = capi.query_knn(X, Q, k)
+        assert np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_pruned_skips_tiles_and_stays_exact(monkeypatch):
+    """On clustered data most score tiles must be skipped (stats), with the answer still equal to the exact search."""
+    import torch
+    from batchelor_b200 import device as dev
+
+    monkeypatch.setenv("B200MNN_PRUNE", "1")
+    monkeypatch.setenv("B200MNN_CLUSTERS", "32")
+    X, Q = synth.pc_batches(2, [60_000, 30_000], d=50, ncomp=16)
+    Xd, Qd = torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda()
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    idx, dist = dev.query_knn(Xd, Qd, 20, stats=stats)
+    s = stats.cpu().numpy()
+    print(f"stats {s}")
+    assert s[2] == 2 and s[0] == 0
+    assert 0 < s[4] < 0.4 * s[6], f"pruning skipped too little: {s[4]} of {s[6]} tiles scored"
+    want_idx, want_dist = capi.Kmknn(X).query(Q, 20)
+    assert int((idx.cpu().numpy() + 1 != want_idx).sum()) == 0
+    assert np.array_equal(dist.cpu().numpy(), want_dist)
+
+
+def test_query_knn_dense_path_still_exact_at_medium_size(monkeypatch):
+    monkeypatch.setenv("B200MNN_PRUNE", "0")
+    X, Q = synth.pc_batches(2, [70_000, 20_000], d=50)
+    got = bb.queryKNN(X, Q, 20)
+    idx, dist = capi.Kmknn(X).query(Q, 20)
+    assert int((got["index"] != idx).sum()) == 0 and np.array_equal(got["distance"], dist)
+
+
 def test_candidate_scoring_error_is_far_inside_the_certificate_bound():
     """The tensor-core scores must approximate the exact squared distances much better than the eps the certificate
     assumes (2^-16 (|q| M + M^2)); otherwise the rescue path would carry the correctness."""
@@ -117,10 +184,10 @@ def test_candidate_scoring_error_is_far_inside_the_certificate_bound():
     ratio = (np.abs(cd2 - exact) / eps[:, None])[valid].max()
     print(f"max |approx-exact| = {err.max():.3e}, max err/eps = {ratio:.3f}")
     assert ratio < 0.25
-    stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
     dev.query_knn(Xd, Qd, 20, stats=stats)
     s = stats.cpu().numpy()
-    assert s[2] == 1 and s[0] == 0, f"tensor path not taken or queries rescued: {s}"
+    assert s[2] >= 1 and s[0] == 0, f"tensor path not taken or queries rescued: {s}"
 
 
 # ---------------------------------------------------------------------------------------------------------------
