@@ -342,6 +342,32 @@ __global__ void __launch_bounds__(256) tile_project_kernel(const double* __restr
     }
 }
 
+// Second tier: the uncertified queries (an unordered device list) regrouped into cluster-pure, padded slots.
+__global__ void list_hist_kernel(const int32_t* __restrict__ list, const int* __restrict__ count, const int32_t* __restrict__ cid,
+                                 int* __restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count) atomicAdd(cnt + cid[list[i]], 1);
+}
+__global__ void list_offsets_kernel(const int* __restrict__ cnt, int C, int* __restrict__ base, int* __restrict__ nslots, int* __restrict__ cursors) {
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int c = 0; c < C; ++c) {
+            base[c] = s;
+            s += ((cnt[c] + CL_TILE - 1) / CL_TILE) * CL_TILE;
+        }
+        *nslots = s;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) cursors[c] = 0;
+}
+__global__ void list_scatter_kernel(const int32_t* __restrict__ list, const int* __restrict__ count, const int32_t* __restrict__ cid,
+                                    const int* __restrict__ base, int* __restrict__ cursors, int32_t* __restrict__ map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *count) return;
+    const int q = list[i];
+    const int c = cid[q];
+    map[base[c] + atomicAdd(cursors + c, 1)] = q;
+}
+
 __global__ void fill_vref_kernel(unsigned long long* __restrict__ vref, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) vref[i] = dkey(-INFINITY);
@@ -435,6 +461,20 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
                                                                                         p.cdist, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
     B200_TRY(build_tile_lists(p, dQ, d, p.qmap, p.nslots, p.nslots_max, qnorm, scale_exp, maxnorm_bits, p.cl_list, p.qoff, stream));
+    return 0;
+}
+
+int regroup_query_list(const ClusterPlan& p, const int32_t* list, const int* count, int64_t max_items, int32_t* map, int64_t max_slots,
+                       int* nslots, int* work /* [3 * CL_MAXC] */, cudaStream_t stream) {
+    B200_CUDA(cudaMemsetAsync(work, 0, sizeof(int) * 3 * CL_MAXC, stream));
+    B200_CUDA(cudaMemsetAsync(map, 0xFF, sizeof(int32_t) * (size_t)max_slots, stream));
+    const unsigned grid = (unsigned)ceil_div(max_items, 256);
+    list_hist_kernel<<<grid, 256, 0, stream>>>(list, count, p.cid_q, work);
+    B200_LAUNCH_CHECK();
+    list_offsets_kernel<<<1, 256, 0, stream>>>(work, p.C, work + CL_MAXC, nslots, work + 2 * CL_MAXC);
+    B200_LAUNCH_CHECK();
+    list_scatter_kernel<<<grid, 256, 0, stream>>>(list, count, p.cid_q, work + CL_MAXC, work + 2 * CL_MAXC, map);
+    B200_LAUNCH_CHECK();
     return 0;
 }
 

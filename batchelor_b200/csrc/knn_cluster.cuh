@@ -40,5 +40,10 @@ int build_tile_lists(const ClusterPlan& plan, const double* dQ, int d, const int
                      const double* qnorm, const int* scale_exp, const unsigned long long* maxnorm_bits, int2* lists, float* qoff,
                      cudaStream_t stream);
 
+// Regroups an unordered device list of query ids (count on the device, at most max_items) into cluster-pure slots padded
+// to multiples of CL_TILE: map[slot] = query or -1, *nslots = slots in use.  max_slots >= max_items + C * CL_TILE.
+int regroup_query_list(const ClusterPlan& plan, const int32_t* list, const int* count, int64_t max_items, int32_t* map, int64_t max_slots,
+                       int* nslots, int* work /* [3 * CL_MAXC] ints */, cudaStream_t stream);
+
 }  // namespace knn
 }  // namespace b200

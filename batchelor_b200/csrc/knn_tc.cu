@@ -841,20 +841,19 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 //    the epilogue runs EIGHT warps, two per scheduler: warps w and w+4 own the same TMEM lane quarter (the same 32
 //    query rows) and each scans one 64-column half of every tile.  A stage is released as soon as both halves are in
 //    registers (TMEM loads take ~30 cycles), so the MMA pipeline always has ~3 tiles of slack.
-//  * Candidate rows are shared by the two warps of a pair: [KEEP sorted keys | pending of warp A | pending of warp
-//    B].  A warp appends only to its own pending segment (no synchronisation on the hit path) and merges it into the
-//    kept keys under a per-pair lock; the row threshold lives in shared memory and the partner picks it up at its
-//    next tile (a stale threshold is only ever too lenient, never wrong).
+//  * Every epilogue warp keeps its OWN candidate list per row (the KEEP best scores of the columns it scanned),
+//    unsorted, in shared memory: a hit replaces the current maximum (one vote to find its holder, one REDUX for the
+//    new maximum = the new threshold).  No pending buffers, no locks between the warps of a pair, and no capacity that
+//    could overflow: the lists of the two warps are merged once, after the stream.  With cluster pruning nearly every
+//    scored tile belongs to the queries' own component, so hits are frequent and their cost -- not the quiet path --
+//    decides the kernel time; the former sorted-list-with-pending-segment scheme spent 5 of 9 k cycles per tile in
+//    bitonic merges and lock waits there.
 constexpr int TS_BN = 128;                   // references per tile
 constexpr int TS_STAGES = 3;                 // accumulator stages in TMEM
 constexpr int TS_B_BOX_BYTES = TS_BN * 128;  // 16 KB
 constexpr int TS_MAX_NBOX = 4;               // A columns: 32 per box, 3*128 accumulator columns -> at most 4 boxes
 constexpr int TS_THREADS = 352;              // warp 0: TMA, warps 1 and 10: MMA issuers (even / odd tiles), warps 2..9: epilogue
 constexpr int TS_EPI_WARPS = 8;
-constexpr int TS_PENDW = 24;                 // pending keys per row and epilogue warp
-// first tiles: scanned by one warp of each pair with a compaction after every chunk; afterwards a row sees on average
-// 64 * KEEP / (128 * boot tiles) = 8 hits per 64 columns, far below the 24 pending slots of a warp
-constexpr int TS_BOOT_TILES_PER_E = 2;
 constexpr int TS_RING = 32;                  // tile-id ring between the producer and its consumers (>= tiles in flight + 2)
 // Pruned search (knn_cluster.cuh): per query tile the reference clusters in ascending order of their lower bound.
 // cl_list == nullptr: dense scan of tiles [tile0, tile1).
@@ -865,13 +864,6 @@ struct PruneArgs {
     int C;
     unsigned long long* visited;   // optional counter: tiles scored by this launch
 };
-template <int E>
-struct TsCand {
-    static constexpr int KEEP = 32 * E;
-    static constexpr int CAP = KEEP + 2 * TS_PENDW;     // >= KEEP + 32: the bootstrap needs room for one full chunk of hits
-    static constexpr int PAIR_KEYS = CAP * ROWPITCH;
-};
-
 __device__ __forceinline__ void umma_f16_ts_impl(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -890,73 +882,143 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const u
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-#ifndef B200_FENCE_STYLE
-#define B200_FENCE_STYLE 1
-#endif
-// Ordering between the two warps of a pair (shared-memory candidate rows, thresholds): acquire/release at CTA scope is
-// all that is needed; __threadfence_block() is a sequentially-consistent fence (MEMBAR.SC.CTA).
-__device__ __forceinline__ void pair_fence() {
-#if B200_FENCE_STYLE == 0
-    __threadfence_block();
-#elif B200_FENCE_STYLE == 1
-    asm volatile("fence.acq_rel.cta;" ::: "memory");
-#else
-    asm volatile("" ::: "memory");
-#endif
+// Order-preserving map float -> uint32 (the high word of make_key) and back.
+__device__ __forceinline__ uint32_t ord_bits(float s) {
+    uint32_t u = __float_as_uint(s);
+    return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
 }
-// Merges the pending keys of every row in `todo` (this warp's segment at position pbase) into the row's kept keys
-// (sorted, full) and publishes the new threshold.  The per-pair lock serialises the two warps' merges.
-template <int E>
-__device__ __forceinline__ void compact_pending(unsigned long long* __restrict__ buf, const int pbase, const int lane, unsigned todo, int& pc,
-                                                volatile float* thr_row, int* lock, long long* mstat = nullptr) {
-    long long m0 = 0;
-    if (mstat) { m0 = clock64(); mstat[1] += 1; mstat[2] += __popc(todo); }
-    {   // warp-uniform acquire (see mbar_wait_u): lane 0 tries, every lane learns the outcome and backs off together
-        const long long t0 = clock64();
-        while (true) {
-            int got = 1;
-            if (lane == 0) got = atomicCAS(lock, 0, 1);
-            got = __shfl_sync(0xffffffffu, got, 0);
-            if (got == 0) break;
-            __nanosleep(100);
-            if (clock64() - t0 > 20000000000LL) __trap();
-        }
+__device__ __forceinline__ float ord_float(uint32_t u) { return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u)); }
+constexpr uint32_t ORD_INF = 0xFF800000u;   // ord_bits(+inf)
+
+// Stages one 32x32 chunk of scores (registers, lane = row) in shared memory, XOR-swizzled so that both these row-wise
+// writes and the column-wise reads of ts_chunk_score are bank-conflict free.
+__device__ __forceinline__ void ts_stage_chunk(const uint32_t (&v)[32], float4* __restrict__ stg, const int lane) {
+#define VF(i) __uint_as_float(v[i])
+#pragma unroll
+    for (int j = 0; j < 8; ++j) stg[j * 32 + (lane ^ j)] = make_float4(VF(4 * j), VF(4 * j + 1), VF(4 * j + 2), VF(4 * j + 3));
+#undef VF
+    __syncwarp();
+}
+// score of (row L, column `lane`) of the staged chunk
+__device__ __forceinline__ float ts_chunk_score(const float4* __restrict__ stg, const int L, const int lane) {
+    const int g = lane >> 2;
+    return reinterpret_cast<const float*>(stg)[((g * 32 + (L ^ g)) << 2) + (lane & 3)];
+}
+// First chunks of a warp: copied straight into segment `seg` of every row's list (no selection needed yet).
+template <int KEEP>
+__device__ __forceinline__ void ts_fill_staged(const int col0, const int seg, uint2* __restrict__ list, const float4* __restrict__ stg, const int lane) {
+#pragma unroll 8
+    for (int L = 0; L < 32; ++L) {
+        const float sc = ts_chunk_score(stg, L, lane);
+        const uint32_t o = ord_bits(sc);
+        list[L * KEEP + seg * 32 + lane] = make_uint2(o, o >= ORD_INF ? 0xFFFFFFFFu : (uint32_t)(col0 + lane));   // padding rows score +inf
     }
     __syncwarp();
-    pair_fence();
-    if (mstat) mstat[0] += clock64() - m0;
-    constexpr int NR = MERGE_ROWS;
-    while (todo) {
-        long long r0 = 0;
-        if (mstat) r0 = clock64();
-        int r[NR];
-        unsigned long long a0[NR], a1[NR], p[NR];
+}
+// Hits of one chunk: for every hitting row L the 32 lanes each look at ONE score of that row; every score below the
+// row's threshold replaces the current maximum of the row's list.  Invariant: thr (register of lane L) == max of list L.
+// One insertion is a chain of dependent warp collectives (SHFL -> VOTE -> REDUX, ~100+ cycles of latency and nothing else
+// to issue), so INS_ROWS rows are processed side by side in branch-free lock step: their chains interleave.
+#ifndef B200_INS_ROWS
+#define B200_INS_ROWS 4
+#endif
+template <int E>
+__device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, float& thr, uint2* __restrict__ list,
+                                                 volatile float* __restrict__ thr_pub, const float4* __restrict__ stg, const int lane, long long* stat) {
+    constexpr int KEEP = 32 * E;
+    constexpr int NR = B200_INS_ROWS;
+    long long tc0 = 0, tc1 = 0, tc2 = 0, tc3 = 0;
+    (void)tc0;
+    if (stat) { stat[0] += 1; stat[1] += __popc(hit); if (__activemask() != 0xffffffffu) stat[8] += 1; tc0 = clock64(); }
+    do {
+        if (stat) tc1 = clock64();
+        int L[NR];
+        unsigned m[NR];
+        uint32_t so[NR], curmax[NR];
+        uint2 e0[NR], e1[NR];
+        unsigned any = 0;
+        float thrL[NR], sc[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            r[i] = todo ? __ffs(todo) - 1 : -1;                    // -1: batch slot unused (computed on row r[0], not stored)
-            todo &= todo - 1;
-            const int rr = r[i] < 0 ? r[0] : r[i];
-            const int c = __shfl_sync(0xffffffffu, pc, rr);
-            a0[i] = buf[lane * ROWPITCH + rr];
-            a1[i] = (E == 2) ? buf[(lane + 32) * ROWPITCH + rr] : EMPTY_KEY;
-            p[i] = (lane < c) ? buf[(pbase + lane) * ROWPITCH + rr] : EMPTY_KEY;
+            L[i] = hit ? __ffs(hit) - 1 : -1;            // -1: slot unused (rides along on row L[0], never stored)
+            hit &= hit - 1;
         }
-        merge_keys<E, NR>(a0, a1, p, false, lane);
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-            if (r[i] >= 0) {   // warp-uniform
-                buf[lane * ROWPITCH + r[i]] = a0[i];
-                if (E == 2) buf[(lane + 32) * ROWPITCH + r[i]] = a1[i];
-                const unsigned long long lastkey = (E == 1) ? a0[i] : a1[i];
-                if (lane == 31) thr_row[r[i]] = (lastkey == EMPTY_KEY) ? __int_as_float(0x7f800000) : key_score(lastkey);
-                if (lane == r[i]) pc = 0;
+            const int LL = L[i] < 0 ? L[0] : L[i];
+            thrL[i] = __shfl_sync(0xffffffffu, thr, LL);
+            sc[i] = ts_chunk_score(stg, LL, lane);
+            e0[i] = list[LL * KEEP + lane];
+            e1[i] = make_uint2(0u, 0u);
+            if (E == 2) e1[i] = list[LL * KEEP + 32 + lane];
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const unsigned mm = __ballot_sync(0xffffffffu, sc[i] < thrL[i]);
+            m[i] = L[i] < 0 ? 0u : mm;
+            so[i] = ord_bits(sc[i]);
+            curmax[i] = ord_bits(thrL[i]);
+            any |= m[i];
+            if (stat) stat[2] += __popc(m[i]);
+        }
+        if (stat) { tc2 = clock64(); stat[5] += tc2 - tc1; }
+        while (any) {   // warp-uniform: one candidate of every row per round, in phases so that the collectives of the rows overlap
+            uint32_t sj[NR], idj[NR];
+            unsigned b0[NR], b1[NR];
+            bool act[NR];
+            any = 0;
+            if (stat) { stat[3] += 1; if (__activemask() != 0xffffffffu) stat[9] += 1; }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                act[i] = m[i] != 0u;
+                const int j = act[i] ? __ffs(m[i]) - 1 : 0;
+                m[i] &= m[i] - 1u;
+                any |= m[i];
+                idj[i] = (uint32_t)(col0 + j);
+                sj[i] = __shfl_sync(0xffffffffu, so[i], j);
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                b0[i] = __ballot_sync(0xffffffffu, e0[i].x == curmax[i]);
+                b1[i] = (E == 2) ? __ballot_sync(0xffffffffu, e1[i].x == curmax[i]) : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i) {
+                const bool doit = act[i] && sj[i] < curmax[i];
+                const bool in0 = doit && (E == 1 || b0[i] != 0u) && lane == __ffs(b0[i]) - 1;
+                e0[i].x = in0 ? sj[i] : e0[i].x;
+                e0[i].y = in0 ? idj[i] : e0[i].y;
+                if (E == 2) {
+                    const bool in1 = doit && b0[i] == 0u && lane == __ffs(b1[i]) - 1;
+                    e1[i].x = in1 ? sj[i] : e1[i].x;
+                    e1[i].y = in1 ? idj[i] : e1[i].y;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NR; ++i)   // unchanged when nothing was replaced
+                curmax[i] = __reduce_max_sync(0xffffffffu, E == 1 ? e0[i].x : max(e0[i].x, e1[i].x));
+        }
+        if (stat) { tc3 = clock64(); stat[6] += tc3 - tc2; }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            if (L[i] >= 0) {   // warp-uniform
+                list[L[i] * KEEP + lane] = e0[i];
+                if (E == 2) list[L[i] * KEEP + 32 + lane] = e1[i];
+                if (lane == L[i]) {
+                    thr = ord_float(curmax[i]);
+                    thr_pub[L[i]] = thr;
+                }
             }
         }
-        if (mstat) { const long long dt = clock64() - r0; mstat[3] += dt; if (dt < mstat[4]) mstat[4] = dt; if (dt > mstat[5]) mstat[5] = dt; }
-    }
-    pair_fence();
-    __syncwarp();
-    if (lane == 0) atomicExch(lock, 0);
+        if (stat) stat[7] += clock64() - tc3;
+    } while (hit);
+    __syncwarp();   // the staging area is reused by the next chunk
+}
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
+    float m = __uint_as_float(v[0]);
+#pragma unroll
+    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+    return m;
 }
 
 template <int E, int NBOX>
@@ -981,16 +1043,14 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     const int lane = threadIdx.x & 31;
     constexpr int A_COLS = NBOX * 32;                      // TMEM columns holding the query operand
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TS_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    constexpr int KEEP = TsCand<E>::KEEP;
+    constexpr int KEEP = 32 * E;
 
     uint8_t* smB = smem;
-    unsigned long long* lists = reinterpret_cast<unsigned long long*>(smB + (size_t)nslot * TS_B_BOX_BYTES);   // [4 pairs][CAP][ROWPITCH]
-    float4* stage_all = reinterpret_cast<float4*>(lists + 4 * TsCand<E>::PAIR_KEYS + 2);                       // [8 warps][8][32]
-    float* thr_s = reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                                // [128]
-    int* dirty_s = reinterpret_cast<int*>(thr_s + BM);                                                         // [128]
-    int* locks = dirty_s + BM;                                                                                 // [4]
-    volatile int* ring = locks + 4;                                                                            // [TS_RING] tile ids, -1 = end
-    float* qoff_s = reinterpret_cast<float*>(locks + 4 + TS_RING);                                             // [128]
+    uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);                             // [8 warps][32 rows][KEEP] (score bits, id)
+    float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 32 * KEEP);                   // [8 warps][8][32]
+    float* thr_s = reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                                // [2 column halves][128] thresholds
+    volatile int* ring = reinterpret_cast<int*>(thr_s + 2 * BM);                                               // [TS_RING] tile ids, -1 = end
+    float* qoff_s = reinterpret_cast<float*>(thr_s + 2 * BM) + TS_RING;                                        // [128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + BM);
     uint64_t* full = bars;                     // [MAX_SLOTS]
     uint64_t* empty = bars + MAX_SLOTS;        // [MAX_SLOTS]
@@ -1025,10 +1085,9 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     }
     if (threadIdx.x < BM) {
         thr_s[threadIdx.x] = __int_as_float(0x7f800000);
-        dirty_s[threadIdx.x] = 0;
+        thr_s[BM + threadIdx.x] = __int_as_float(0x7f800000);
         qoff_s[threadIdx.x] = (P.cl_list && (int64_t)m0 + threadIdx.x < nq_eff) ? P.qoff[m0 + threadIdx.x] : __int_as_float(0xff800000);
     }
-    if (threadIdx.x < 4) locks[threadIdx.x] = 0;
     if (warp == 1) {
         tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
         tmem_relinquish();
@@ -1052,6 +1111,10 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                 ring[seq & (TS_RING - 1)] = tile;
 #pragma unroll
                 for (int b = 0; b < NBOX; ++b) {
+                    if (tile < 0 && b > 0) {   // an end marker arms only its first box (nobody consumes, hence frees, the others)
+                        if (++slot == nslot) { slot = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_wait(smem_u32(&empty[slot]), phase ^ 1);   // lane 0 only
                     if (tile < 0 || dbg_mode == 3) {
                         mbar_arrive(smem_u32(&full[slot]));
@@ -1082,7 +1145,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
 #pragma unroll
                         for (int r = lane; r < BM; r += 32) {
                             const float qo = qoff_s[r];
-                            if (qo > __int_as_float(0xff800000)) m = fmaxf(m, __fadd_ru(thr_v[r], qo));
+                            if (qo > __int_as_float(0xff800000)) m = fmaxf(m, __fadd_ru(fminf(thr_v[r], thr_v[BM + r]), qo));
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -1152,30 +1215,22 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         }
     } else {
         // ===================== epilogue: warps 2..9 =====================
-        const int grp = (warp - 2) >> 2;          // 0: columns 0..63 of every tile (+ bootstrap), 1: columns 64..127
-        const int pr = (warp - 2) & 3;            // pair: warps pr+2 and pr+6
+        const int grp = (warp - 2) >> 2;          // 0: columns 0..63 of every tile, 1: columns 64..127
+        const int pr = (warp - 2) & 3;            // pair: warps pr+2 and pr+6 read the same 32 TMEM lanes (query rows)
         const int q4 = warp & 3;                  // TMEM lane quarter both warps of the pair may access
         const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-        unsigned long long* mybuf = lists + (size_t)pr * TsCand<E>::PAIR_KEYS;
+        uint2* mylist = lists + (size_t)(warp - 2) * 32 * KEEP;                      // this warp's own candidate lists
         float4* stg = stage_all + (size_t)(warp - 2) * 8 * 32;
-        volatile float* thr_row = thr_s + q4 * 32;
-        int* dirty_row = dirty_s + q4 * 32;
-        int* lock = locks + pr;
+        volatile float* thr_pub = thr_s + grp * BM + q4 * 32;                        // read by the producer's stop test
         const uint32_t lane_acc = acc_base + lane_sel;
-        bool dirty = false;
-        long long acc_t[4] = {0, 0, 0, 0};   // measurement aid (trace only): tfull wait, TMEM load, scan, merge
-        int stat[3] = {0, 0, 0};
-        long long mstat[6] = {0, 0, 0, 0, 1LL << 60, 0};   // lock wait cycles, merge calls, merged rows, row cycles sum/min/max
+        long long acc_t[4] = {0, 0, 0, 0};   // measurement aid (trace only): tfull wait, TMEM load, scan + hits
+        long long stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // measurement aid (trace only), see ts_insert_hits
         uint32_t v0[32], v1[32];
-        constexpr int NBOOT = TS_BOOT_TILES_PER_E * E;
-        // Tiles arrive in the producer's order; entry seq of the tile-id ring names the tile in accumulator stage
-        // seq % TS_STAGES (-1: end of the stream; both warps of a pair see it at the same seq).
-        int seq = 0, stage = 0;
-        uint32_t par = 0;
-        bool ended = false;
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) mylist[i * 32 + lane] = make_uint2(ORD_INF, 0xFFFFFFFFu);   // empty lists: score +inf, id -1
 
         if (grp == 0) {
-            // (1) this thread's query row -> TMEM (A operand of every MMA of this CTA)
+            // this thread's query row -> TMEM (A operand of every MMA of this CTA)
             const int64_t j = (int64_t)m0 + q4 * 32 + lane;
             int64_t src = j;                                       // rows past nq are zero padding of opA
             if (qmap) src = (j < nq_eff) ? (int64_t)qmap[j] : -1;
@@ -1190,61 +1245,21 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(aready));
-            // (2) bootstrap: whole tiles, a compaction after every chunk that overfills a row
-            int cnt = 0;
-            bool sorted = false;
-            float thr = __int_as_float(0x7f800000);
-            for (int tb = 0; tb < NBOOT; ++tb) {
-                mbar_wait_u(smem_u32(&tfull[stage]), par);
-                tc_fence_after();
-                const int tile = ring[seq & (TS_RING - 1)];
-                if (tile < 0) { ended = true; break; }
-                const int colbase = tile * TS_BN;
-                const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
-#pragma unroll 1
-                for (int c = 0; c < TS_BN / 32; ++c) {
-                    tmem_ld32(tbase + (uint32_t)(c * 32), v0);
-                    tmem_ld_wait();
-                    if (c == TS_BN / 32 - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
-                    }
-                    if (dbg_mode != 1) {
-                        scan_chunk<E>(v0, colbase + c * 32, thr, cnt, dirty, mybuf, stg, lane);
-                        if (__any_sync(0xffffffffu, cnt > KEEP)) compact_rows<E>(mybuf, lane, KEEP, thr, cnt, sorted);
-                    }
-                }
-                ++seq;
-                if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
-            }
-            compact_rows<E>(mybuf, lane, -1, thr, cnt, sorted);   // every row sorted (padded with EMPTY_KEY), thresholds final
-            thr_row[lane] = (dbg_mode == 8) ? __int_as_float(0xff800000) : thr;   // 8: measurement aid, no hit ever
-        } else {
-            for (int tb = 0; tb < NBOOT; ++tb) {
-                mbar_wait_u(smem_u32(&tfull[stage]), par);
-                if (ring[seq & (TS_RING - 1)] < 0) { ended = true; break; }
-                if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
-                ++seq;
-                if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
-            }
         }
-        pair_fence();
-        pair_barrier(1 + pr);
+        __syncwarp();
 
-        // (3) steady state: 64 columns per warp and tile
-        int pc = 0;                                     // keys in this warp's pending segment of row `lane`
-        const int pbase = KEEP + grp * TS_PENDW;
-        unsigned long long* pend = mybuf + (size_t)pbase * ROWPITCH;
-        // Quiet tiles (no score below any threshold of the warp's rows -- the common case) must stay a short dependent
-        // chain: wait, two TMEM loads, release, min tree, ONE vote.  Stage/parity are carried in registers, the row
-        // threshold is re-read from shared memory only after a hit (own merge) or every 8th tile (partner's merges: a
-        // stale threshold is merely lenient), and the pending counts are only inspected after a hit.
+        // Tiles arrive in the producer's order; entry seq of the tile-id ring names the tile in accumulator stage
+        // seq % TS_STAGES (-1: end of the stream).  Per tile this warp scans 64 columns.  Quiet chunks (no score below
+        // any threshold of the warp's rows -- the common case of a dense scan) stay a short dependent chain: wait, two
+        // TMEM loads, release, two min trees, ONE vote.
+        int seq = 0, stage = 0;
+        uint32_t par = 0;
+        int filled = 0;                                 // chunks copied straight into the lists (the first E)
+        float fillmax = __int_as_float(0xff800000);
+        float thr = __int_as_float(0x7f800000);         // == max of this lane's row list once the list is full
         const bool skip_read = dbg_mode == 1;
-        float thr = thr_row[lane];
-        int steady = 0;
-        while (!ended) {
-            long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        while (true) {
+            long long c0 = 0, c1 = 0, c2 = 0;
             if (trace) c0 = clock64();
             mbar_wait_u(smem_u32(&tfull[stage]), par);
             tc_fence_after();
@@ -1262,54 +1277,73 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
             if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
             ++seq;
-            ++steady;
             if (trace) c2 = clock64();
             if (skip_read) continue;
-            const bool hit = scan_pair<TS_PENDW>(v0, v1, tile * TS_BN + grp * 64, thr, pc, dirty, pend, stg, lane, trace ? stat : nullptr);
-            if (trace) c3 = clock64();
-            if (hit) {   // warp-uniform
-                // early tiles still see several hits per row and pair of chunks: start every pair with an empty segment
-                const int limit = (seq < 32) ? 0 : TS_PENDW / 2;
-                const unsigned todo = __ballot_sync(0xffffffffu, pc > limit);
-                if (todo) compact_pending<E>(mybuf, pbase, lane, todo, pc, thr_row, lock, trace ? mstat : nullptr);
-                thr = thr_row[lane];
-            } else if ((seq & 7) == 0) {
-                thr = thr_row[lane];
+            const int col0 = tile * TS_BN + grp * 64;
+            const float ma = chunk_min(v0), mb = chunk_min(v1);
+            if (filled == E && !__any_sync(0xffffffffu, fminf(ma, mb) < thr)) continue;   // quiet tile
+            // ONE copy of the fill / insertion code for both chunks (the loop is not unrolled): the hit path is long, and
+            // with a copy per call site the eight epilogue warps thrashed the instruction cache (IPC 0.2).
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                if (filled < E) {   // warp-uniform: the first E chunks of this warp go straight into the lists
+                    float mx;
+                    if (c == 0) { ts_stage_chunk(v0, stg, lane); mx = chunk_max(v0); }
+                    else { ts_stage_chunk(v1, stg, lane); mx = chunk_max(v1); }
+                    ts_fill_staged<KEEP>(col0 + 32 * c, filled, mylist, stg, lane);
+                    fillmax = fmaxf(fillmax, mx);
+                    if (++filled == E) { thr = (dbg_mode == 8) ? __int_as_float(0xff800000) : fillmax; thr_pub[lane] = thr; }
+                    continue;
+                }
+                const unsigned h = __ballot_sync(0xffffffffu, (c == 0 ? ma : mb) < thr);   // thr may just have tightened
+                if (h == 0u) continue;
+                if (c == 0) ts_stage_chunk(v0, stg, lane);
+                else ts_stage_chunk(v1, stg, lane);
+                ts_insert_staged<E>(h, col0 + 32 * c, thr, mylist, thr_pub, stg, lane, trace ? stat : nullptr);
             }
-            if (trace) {
-                acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; acc_t[2] += c3 - c2; acc_t[3] += clock64() - c3;
-            }
+            if (trace) { acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; acc_t[2] += clock64() - c2; }
         }
-        {   // end of the stream: merge what is still pending
-            const unsigned todo = __ballot_sync(0xffffffffu, pc > 0);
-            if (todo) compact_pending<E>(mybuf, pbase, lane, todo, pc, thr_row, lock, trace ? mstat : nullptr);
-        }
-        if (dirty) dirty_row[lane] = 1;
-        pair_fence();
-        pair_barrier(1 + pr);
+        __syncwarp();
+        pair_barrier(1 + pr);   // both lists of every row of the pair are final
         if (trace && lane == 0) {
             for (int i = 0; i < 4; ++i) dbg_ts[(warp - 2) * 8 + i] = acc_t[i];
             for (int i = 0; i < 3; ++i) dbg_ts[(warp - 2) * 8 + 4 + i] = stat[i];
-            dbg_ts[(warp - 2) * 8 + 7] = steady;
-            for (int i = 0; i < 6; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = mstat[i];
+            dbg_ts[(warp - 2) * 8 + 7] = seq;
+            for (int i = 0; i < 7; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = stat[3 + i];
         }
-        // (4) output: the two warps of a pair write 16 rows each
+        // Output: the two warps of a pair merge and write 16 rows each.  The KEEP best of the union of both lists are the
+        // row's candidates and the KEEP-th best score its threshold: a rejected or evicted score was >= the list maximum
+        // of the warp that saw it, which only ever decreases and ends >= that KEEP-th best score.
+        const uint2* listA = lists + (size_t)pr * 32 * KEEP;
+        const uint2* listB = lists + (size_t)(pr + 4) * 32 * KEEP;
         const int64_t rowbase = (int64_t)m0 + q4 * 32;
         const int64_t sbase = (int64_t)blockIdx.y * nq;
 #pragma unroll 1
         for (int r = grp * 16; r < grp * 16 + 16; ++r) {
             const int64_t row = rowbase + r;
-            if (row < nq_eff) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const unsigned long long key = mybuf[(lane + 32 * e) * ROWPITCH + r];
-                    const int64_t o = (sbase + row) * (32 * E) + lane + 32 * e;
-                    cand_idx[o] = (int32_t)(uint32_t)key;
-                    if (cand_score) cand_score[o] = key_score(key);
-                }
+            if (row >= nq_eff) break;   // warp-uniform
+            unsigned long long a0[1], a1[1], pk[1];
+            uint2 t = listA[r * KEEP + lane];
+            a0[0] = ((unsigned long long)t.x << 32) | t.y;
+            a1[0] = EMPTY_KEY;
+            if (E == 2) { t = listA[r * KEEP + 32 + lane]; a1[0] = ((unsigned long long)t.x << 32) | t.y; }
+            t = listB[r * KEEP + lane];
+            pk[0] = ((unsigned long long)t.x << 32) | t.y;
+            merge_keys<E, 1>(a0, a1, pk, true, lane);
+            if (E == 2) {
+                t = listB[r * KEEP + 32 + lane];
+                pk[0] = ((unsigned long long)t.x << 32) | t.y;
+                merge_keys<E, 1>(a0, a1, pk, false, lane);
             }
+            const int64_t o = (sbase + row) * KEEP + lane;
+            cand_idx[o] = (int32_t)(uint32_t)a0[0];
+            if (cand_score) cand_score[o] = key_score(a0[0]);
+            if (E == 2) {
+                cand_idx[o + 32] = (int32_t)(uint32_t)a1[0];
+                if (cand_score) cand_score[o + 32] = key_score(a1[0]);
+            }
+            if (lane == 31) thr_out[sbase + row] = key_score(E == 1 ? a0[0] : a1[0]);   // +inf while fewer than KEEP references were seen
         }
-        if (grp == 0 && rowbase + lane < nq_eff) thr_out[sbase + rowbase + lane] = dirty_row[lane] ? __int_as_float(0xff800000) : thr_row[lane];
         tc_fence_before();
     }
     __syncthreads();
@@ -1741,8 +1775,8 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 }
 
 static size_t ts_smem_bytes(int nslot, int E) {
-    return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + (size_t)(4 * (32 * E + 2 * TS_PENDW) * ROWPITCH + 2) * 8 +
-           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)BM * 8 + 16 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
+    return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * 32 * (32 * E) * 8 +
+           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)2 * BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
            (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
 }
 // TS variant: the operand must fit the TMEM columns next to the accumulators and at least nbox+1 reference boxes must
@@ -1886,10 +1920,14 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     ClusterPlan plan;
     int2* lists2 = nullptr;
     float* qoff2 = nullptr;
+    int32_t* qmap2 = nullptr;   // second tier: the uncertified queries regrouped by cluster
+    int* work2 = nullptr;
     if (use_prune) {
         B200_TRY(build_cluster_plan(dX, n, dQ, nq, d, nclusters, qnorm, scale_exp, maxnorm_bits, ws, stream, &plan));
         lists2 = ws.get<int2>((size_t)(nslots / CL_TILE) * nclusters);
         qoff2 = ws.get<float>((size_t)nslots);
+        qmap2 = ws.get<int32_t>((size_t)nslots);
+        work2 = ws.get<int>((size_t)3 * CL_MAXC + 4);
         if (!ws.ok()) return B200MNN_ENOMEM;
     }
     prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm, nullptr, bmax_bits,
@@ -2036,8 +2074,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
                     fprintf(stderr, "epilogue warp %d (%s half), cycles/tile: tfull wait %.0f, TMEM load %.0f, scan %.0f, merge %.0f; %lld tiles, %lld hit chunks, %lld hit rows, %lld keys\n",
                             w, w < 4 ? "left" : "right", a[0] / nt, a[1] / nt, a[2] / nt, a[3] / nt, a[7], a[4], a[5], a[6]);
                     const long long* m = h + 64 + w * 8;
-                    fprintf(stderr, "    merges: %lld calls, %lld rows, lock wait %.0f cycles/call; cycles per batch: mean %.0f min %lld max %lld\n", m[1], m[2],
-                            m[1] ? (double)m[0] / m[1] : 0.0, m[2] ? (double)m[3] / m[2] : 0.0, m[4], m[5]);
+                    fprintf(stderr, "    insertion: %lld rounds; cycles: staging %lld, row set-up %lld, rounds %lld, stores %lld; entered diverged %lld times, rounds diverged %lld\n",
+                            m[0], m[1], m[2], m[3], m[4], m[5], m[6]);
                     const long long* ps = h + 128 + w * 4;
                     if (ps[3]) fprintf(stderr, "    in-situ dependent-chain latency: SHFL+IADD %.1f, LDS %.1f cycles/op (%lld probes)\n",
                                        (double)ps[0] / (32.0 * ps[3]), (double)ps[2] / (16.0 * ps[3]), ps[3]);
@@ -2093,11 +2131,19 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     const int32_t* rescue_list = flag_list;
     if (two_tier && !fast_only_env) {
         // tier 2: the flagged queries again, three-term schedule, same grid (CTAs past the flag count exit immediately)
-        if (use_prune)
-            B200_TRY(build_tile_lists(plan, dQ, d, flag_list, flag_count, nslots, qnorm, scale_exp, maxnorm_bits, lists2, qoff2, stream));
-        B200_TRY(launch_candidates(false, flag_list, flag_count, prune2, false));
+        const int32_t* qm2 = flag_list;
+        const int* qc2 = flag_count;
+        if (use_prune) {
+            // cluster-pure tiles again: a tile that mixed clusters would meet each row's own cluster late, with loose thresholds
+            int* nslots2 = work2 + 3 * CL_MAXC;
+            B200_TRY(regroup_query_list(plan, flag_list, flag_count, nq, qmap2, nslots, nslots2, work2, stream));
+            B200_TRY(build_tile_lists(plan, dQ, d, qmap2, nslots2, nslots, qnorm, scale_exp, maxnorm_bits, lists2, qoff2, stream));
+            qm2 = qmap2;
+            qc2 = nslots2;
+        }
+        B200_TRY(launch_candidates(false, qm2, qc2, prune2, false));
         rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
-                                                             d_dist, flag_count2, flag_list2, nullptr, flag_list, flag_count, 0, qerr, bmax_bits, refmap);
+                                                             d_dist, flag_count2, flag_list2, nullptr, qm2, qc2, 0, qerr, bmax_bits, refmap);
         B200_LAUNCH_CHECK();
         rescue_count = flag_count2;
         rescue_list = flag_list2;
