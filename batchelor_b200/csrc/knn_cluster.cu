@@ -45,34 +45,63 @@ __global__ void gather_sample_kernel(const double* __restrict__ X, int64_t n, in
     S[e] = X[((i * n) / m) * d + t];
 }
 
-// Farthest-point seeding over every (m / mf)-th sample row: one block, one warp per row and step.
-__global__ void __launch_bounds__(1024) fps_seed_kernel(const double* __restrict__ S, int m, int d, int mf, int C, double* cen) {
-    __shared__ double mind[FPS_MAX];
+// Transposed copy of every (m / mf)-th sample row: T[t][i], so that the seeding below reads coalesced.
+__global__ void transpose_subset_kernel(const double* __restrict__ S, int m, int d, int mf, double* __restrict__ T) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= mf * d) return;
+    const int t = e / mf, i = e - t * mf;
+    T[e] = S[(size_t)i * (m / mf) * d + t];
+}
+
+// Farthest-point seeding over the subset: one block, FPS_ROWS rows per thread, running minimum distances in registers.
+constexpr int FPS_ROWS = FPS_MAX / 1024;
+__global__ void __launch_bounds__(1024) fps_seed_kernel(const double* __restrict__ T, int d, int mf, int C, double* cen) {
     __shared__ double wv[32];
     __shared__ int wi[32];
     __shared__ int pick;
+    extern __shared__ double cj[];   // [d] the newest centroid
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int step = m / mf;
-    for (int i = tid; i < mf; i += 1024) mind[i] = INFINITY;
+    double mind[FPS_ROWS];
+#pragma unroll
+    for (int r = 0; r < FPS_ROWS; ++r) mind[r] = INFINITY;
     if (tid == 0) pick = 0;
     __syncthreads();
     for (int j = 0; j < C; ++j) {
-        const double* src = S + (size_t)pick * step * d;
-        for (int t = tid; t < d; t += 1024) cen[(size_t)j * d + t] = src[t];
+        const int pk = pick;
+        for (int t = tid; t < d; t += 1024) {
+            const double v = T[(size_t)t * mf + pk];
+            cj[t] = v;
+            cen[(size_t)j * d + t] = v;
+        }
         __syncthreads();
         if (j == C - 1) break;
-        const double* cj = cen + (size_t)j * d;
+        double acc[FPS_ROWS];
+#pragma unroll
+        for (int r = 0; r < FPS_ROWS; ++r) acc[r] = 0.0;
+        for (int t = 0; t < d; ++t) {
+            const double c = cj[t];
+#pragma unroll
+            for (int r = 0; r < FPS_ROWS; ++r) {
+                const int i = tid + r * 1024;
+                const double df = (i < mf ? T[(size_t)t * mf + i] : c) - c;
+                acc[r] = fma(df, df, acc[r]);
+            }
+        }
         double bv = -1.0;
         int bi = 0x7fffffff;
-        for (int i = warp; i < mf; i += 32) {
-            const double* x = S + (size_t)i * step * d;
-            double acc = 0.0;
-            for (int t = lane; t < d; t += 32) { const double df = x[t] - cj[t]; acc += df * df; }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            const double v = fmin(mind[i], acc);
-            if (lane == 0) mind[i] = v;
-            if (v > bv) { bv = v; bi = i; }
+        for (int r = 0; r < FPS_ROWS; ++r) {
+            const int i = tid + r * 1024;
+            if (i < mf) {
+                mind[r] = fmin(mind[r], acc[r]);
+                if (mind[r] > bv) { bv = mind[r]; bi = i; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
         if (lane == 0) { wv[warp] = bv; wi[warp] = bi; }
         __syncthreads();
@@ -87,29 +116,42 @@ __global__ void __launch_bounds__(1024) fps_seed_kernel(const double* __restrict
     }
 }
 
-// Nearest centroid of one row held in shared memory (pitch-free pointer), 4 centroids per pass.
-__device__ __forceinline__ int nearest_centroid(const double* __restrict__ x, int d, int C, const double* __restrict__ cen,
+// Centroids transposed into shared memory ([t][c], c fastest) and the dot products of one row with 16 of them: per
+// dimension one row element and eight broadcast 16-byte loads feed sixteen FMAs.
+__device__ __forceinline__ void load_centroids_t(const double* __restrict__ cen, int C, int d, double* cenT) {
+    for (int e = threadIdx.x; e < C * d; e += blockDim.x) {
+        const int c = e / d, t = e - c * d;
+        cenT[t * C + c] = cen[e];
+    }
+}
+__device__ __forceinline__ void dots16(const double* __restrict__ x, int d, int C, const double* __restrict__ cenT, int c0, double (&a)[16]) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) a[u] = 0.0;
+    for (int t = 0; t < d; ++t) {
+        const double xv = x[t];
+        const double2* cp = reinterpret_cast<const double2*>(cenT + t * C + c0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double2 cv = cp[u];
+            a[2 * u] = fma(xv, cv.x, a[2 * u]);
+            a[2 * u + 1] = fma(xv, cv.y, a[2 * u + 1]);
+        }
+    }
+}
+
+// Nearest centroid of one row held in shared memory (C is a multiple of 16).
+__device__ __forceinline__ int nearest_centroid(const double* __restrict__ x, int d, int C, const double* __restrict__ cenT,
                                                 const double* __restrict__ cnorm) {
     double best = INFINITY;
     int bi = 0;
-    for (int c0 = 0; c0 < C; c0 += 4) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const double* p0 = cen + (size_t)c0 * d;
-        const double* p1 = p0 + d;
-        const double* p2 = p1 + d;
-        const double* p3 = p2 + d;
-        for (int t = 0; t < d; ++t) {
-            const double xv = x[t];
-            a0 = fma(xv, __ldg(p0 + t), a0);
-            a1 = fma(xv, __ldg(p1 + t), a1);
-            a2 = fma(xv, __ldg(p2 + t), a2);
-            a3 = fma(xv, __ldg(p3 + t), a3);
+    for (int c0 = 0; c0 < C; c0 += 16) {
+        double a[16];
+        dots16(x, d, C, cenT, c0, a);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const double sc = cnorm[c0 + u] - 2.0 * a[u];
+            if (sc < best) { best = sc; bi = c0 + u; }
         }
-        const double s0 = cnorm[c0] - 2.0 * a0, s1 = cnorm[c0 + 1] - 2.0 * a1, s2 = cnorm[c0 + 2] - 2.0 * a2, s3 = cnorm[c0 + 3] - 2.0 * a3;
-        if (s0 < best) { best = s0; bi = c0; }
-        if (s1 < best) { best = s1; bi = c0 + 1; }
-        if (s2 < best) { best = s2; bi = c0 + 2; }
-        if (s3 < best) { best = s3; bi = c0 + 3; }
     }
     return bi;
 }
@@ -136,13 +178,15 @@ __global__ void __launch_bounds__(CL_TILE) lloyd_accum_kernel(const double* __re
                                                             const double* __restrict__ cen, const double* __restrict__ cnorm,
                                                             double* __restrict__ sums, int* __restrict__ counts) {
     extern __shared__ double rows[];
+    double* cenT = rows + CL_TILE * dp;
     const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
     stage_rows(S, row0, m, d, dp, rows);
+    load_centroids_t(cen, C, d, cenT);
     __syncthreads();
     const int64_t i = row0 + threadIdx.x;
     if (i >= m) return;
     const double* x = rows + threadIdx.x * dp;
-    const int c = nearest_centroid(x, d, C, cen, cnorm);
+    const int c = nearest_centroid(x, d, C, cenT, cnorm);
     for (int t = 0; t < d; ++t) atomicAdd(sums + (size_t)c * d + t, x[t]);
     atomicAdd(counts + c, 1);
 }
@@ -174,14 +218,16 @@ __global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restric
                                                        const double* __restrict__ cen, const double* __restrict__ cnorm,
                                                        int32_t* __restrict__ cid, int* __restrict__ counts) {
     extern __shared__ double rows[];
+    double* cenT = rows + CL_TILE * dp;
     const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
     stage_rows(X, row0, n, d, dp, rows);
+    load_centroids_t(cen, C, d, cenT);
     __syncthreads();
     const int64_t i = row0 + threadIdx.x;
     const bool valid = i < n;
     int c = -1;
     if (valid) {
-        c = nearest_centroid(rows + threadIdx.x * dp, d, C, cen, cnorm);
+        c = nearest_centroid(rows + threadIdx.x * dp, d, C, cenT, cnorm);
         cid[i] = c;
     }
     // warp-aggregated histogram
@@ -224,56 +270,48 @@ __global__ void scatter_kernel(const int32_t* __restrict__ cid, int64_t n, const
 // ---------------------------------------------------------------------------------------------------------------
 // Projections of a tile's rows on the centroid axes
 // ---------------------------------------------------------------------------------------------------------------
-// Block = 256 threads, 128 rows: thread (r = tid & 127, h = tid >> 7) handles the clusters [h*C/2, (h+1)*C/2) of row r.
+// Block = 128 threads, one row each, every cluster in passes of 16 (dots16).
 // MODE 0 (reference tile): vref[P][c] = max over rows of (x.c_c - x.c_P) / D(P,c) + margin   (P = the tile's cluster)
 // MODE 1 (query tile)    : LB[c] = min over rows of -ext_c(P_r) - (q.c_c - q.c_P_r) / D(P_r,c) - margin, then the sorted
 //                          cluster list and the per-slot score offsets.
 template <int MODE>
-__global__ void __launch_bounds__(256) tile_project_kernel(const double* __restrict__ X, int d, int dp, int C, const int32_t* __restrict__ map,
-                                                         const int* __restrict__ count, const int32_t* __restrict__ cid,
-                                                         const double* __restrict__ cen, const double* __restrict__ cdist,
-                                                         unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
-                                                         const double* __restrict__ qnorm, const int* __restrict__ scale_exp,
-                                                         int2* __restrict__ lists, float* __restrict__ qoff) {
-    extern __shared__ double rows[];                 // [128][dp]
+__global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __restrict__ X, int d, int dp, int C, const int32_t* __restrict__ map,
+                                                             const int* __restrict__ count, const int32_t* __restrict__ cid,
+                                                             const double* __restrict__ cen, const double* __restrict__ cdist,
+                                                             unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
+                                                             const double* __restrict__ qnorm, const int* __restrict__ scale_exp,
+                                                             int2* __restrict__ lists, float* __restrict__ qoff) {
+    extern __shared__ double rows[];                 // [128][dp] rows, then [d][C] transposed centroids
+    double* cenT = rows + CL_TILE * dp;
     __shared__ unsigned long long red[CL_MAXC];
     __shared__ int src_s[CL_TILE];
     const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
     if (count && row0 >= (int64_t)*count) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < CL_TILE) src_s[tid] = (!count || row0 + tid < (int64_t)*count) ? map[row0 + tid] : -1;
-    for (int c = tid; c < CL_MAXC; c += 256) red[c] = (MODE == 0) ? dkey(-INFINITY) : dkey(INFINITY);
+    src_s[tid] = (!count || row0 + tid < (int64_t)*count) ? map[row0 + tid] : -1;
+    for (int c = tid; c < CL_MAXC; c += CL_TILE) red[c] = (MODE == 0) ? dkey(-INFINITY) : dkey(INFINITY);
     __syncthreads();
     if (MODE == 0 && src_s[0] < 0) return;           // clusters are padded at their end: an empty first row = an unused tile
-    for (int r = warp; r < CL_TILE; r += 8) {
+    for (int r = warp; r < CL_TILE; r += CL_TILE / 32) {
         const int64_t s = src_s[r];
         for (int t = lane; t < d; t += 32) rows[r * dp + t] = (s >= 0) ? X[s * d + t] : 0.0;
     }
+    load_centroids_t(cen, C, d, cenT);
     __syncthreads();
-    const int r = tid & 127, h = tid >> 7;
-    const int src = src_s[r];
+    const int src = src_s[tid];
     const bool valid = src >= 0;
     const int P = valid ? cid[src] : 0;
-    const double* x = rows + r * dp;
+    const double* x = rows + tid * dp;
     const double M = sqrt(__longlong_as_double((long long)*maxnorm_bits));
     double gP = 0.0, xn = 0.0;
-    {
-        const double* cp = cen + (size_t)P * d;
-        for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, __ldg(cp + t), gP); xn = fma(xv, xv, xn); }
-    }
+    for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, cenT[t * C + P], gP); xn = fma(xv, xv, xn); }
     const double mg_num = 1e-11 * (sqrt(xn) + M) * M;   // >= 1000x the rounding error of the two dot products
     const double tiny = 1e-5 * M;
-    const int cbeg = h * (C / 2), cend = cbeg + C / 2;
-    for (int c0 = cbeg; c0 < cend; c0 += 4) {
-        double a[4] = {0.0, 0.0, 0.0, 0.0};
-        const double* p0 = cen + (size_t)c0 * d;
-        for (int t = 0; t < d; ++t) {
-            const double xv = x[t];
+    for (int c0 = 0; c0 < C; c0 += 16) {
+        double a[16];
+        dots16(x, d, C, cenT, c0, a);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = fma(xv, __ldg(p0 + (size_t)u * d + t), a[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 16; ++u) {
             const int c = c0 + u;
             const double D = cdist[(size_t)P * C + c];
             double val;
@@ -299,7 +337,7 @@ __global__ void __launch_bounds__(256) tile_project_kernel(const double* __restr
     __syncthreads();
     if (MODE == 0) {
         const int Pt = cid[src_s[0]];
-        for (int c = tid; c < C; c += 256)
+        for (int c = tid; c < C; c += CL_TILE)
             if (c != Pt) atomicMax(&vref[(size_t)Pt * C + c], red[c]);
         return;
     }
@@ -307,38 +345,47 @@ __global__ void __launch_bounds__(256) tile_project_kernel(const double* __restr
     const double S2 = scalbn(1.0, 2 * (*scale_exp));
     int CP = 1;
     while (CP < C) CP <<= 1;
-    unsigned long long key = ~0ull;
-    if (tid < C) {
-        const double LB = dkey_inv(red[tid]);
-        float lb;
-        if (!(LB > 0.0)) lb = 0.f;
-        else if (isinf(LB)) lb = __int_as_float(0x7f800000);
-        else lb = __double2float_rd(S2 * LB * LB * (1.0 - 1e-6));
-        key = ((unsigned long long)__float_as_uint(lb) << 32) | (unsigned)tid;
+    unsigned long long keys[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = tid + h * CL_TILE;
+        keys[h] = ~0ull;
+        if (c < C) {
+            const double LB = dkey_inv(red[c]);
+            float lb;
+            if (!(LB > 0.0)) lb = 0.f;
+            else if (isinf(LB)) lb = __int_as_float(0x7f800000);
+            else lb = __double2float_rd(S2 * LB * LB * (1.0 - 1e-6));
+            keys[h] = ((unsigned long long)__float_as_uint(lb) << 32) | (unsigned)c;
+        }
     }
     __syncthreads();
-    if (tid < CP) red[tid] = key;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (tid + h * CL_TILE < CP) red[tid + h * CL_TILE] = keys[h];
     __syncthreads();
     for (int k = 2; k <= CP; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            if (tid < CP) {
-                const int partner = tid ^ j;
-                if (partner > tid) {
-                    const unsigned long long a0 = red[tid], b0 = red[partner];
-                    const bool up = (tid & k) == 0;
-                    if ((a0 > b0) == up) { red[tid] = b0; red[partner] = a0; }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = tid + h * CL_TILE;
+                const int partner = i ^ j;
+                if (i < CP && partner > i) {
+                    const unsigned long long a0 = red[i], b0 = red[partner];
+                    const bool up = (i & k) == 0;
+                    if ((a0 > b0) == up) { red[i] = b0; red[partner] = a0; }
                 }
             }
             __syncthreads();
         }
     }
-    if (tid < C) {
-        const unsigned long long kk = red[tid];
-        lists[(size_t)blockIdx.x * C + tid] = make_int2((int)(unsigned)kk, (int)(unsigned)(kk >> 32));
+    for (int c = tid; c < C; c += CL_TILE) {
+        const unsigned long long kk = red[c];
+        lists[(size_t)blockIdx.x * C + c] = make_int2((int)(unsigned)kk, (int)(unsigned)(kk >> 32));
     }
-    if (tid < CL_TILE) {
-        const int s = src_s[tid];
-        qoff[row0 + tid] = (s >= 0) ? __double2float_ru(S2 * qnorm[s] * (1.0 + 1e-6)) : __int_as_float(0xff800000);
+    {
+        const int s2 = src_s[tid];
+        qoff[row0 + tid] = (s2 >= 0) ? __double2float_ru(S2 * qnorm[s2] * (1.0 + 1e-6)) : __int_as_float(0xff800000);
     }
 }
 
@@ -382,13 +429,13 @@ static int set_smem(const void* fn, size_t bytes) {
 
 int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int C, const double* qnorm, const int* scale_exp,
                        const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream, ClusterPlan* plan) {
-    if (C < 8 || C > CL_MAXC || (C & (C - 1)) != 0) return fail(B200MNN_EINVAL, "internal: cluster count must be a power of two in [8, 256]");
+    if (C < 16 || C > CL_MAXC || (C & (C - 1)) != 0) return fail(B200MNN_EINVAL, "internal: cluster count must be a power of two in [16, 256]");
     int m = (int)std::min<int64_t>(n, SAMPLE_MAX);
     const int mf = std::min(m, FPS_MAX);
     m = (m / mf) * mf;          // the seeding walks the sample with an integer stride
     if (mf < C) return fail(B200MNN_EINVAL, "internal: too few rows for the requested number of clusters");
     const int dp = d | 1;
-    const size_t row_smem = (size_t)CL_TILE * dp * sizeof(double);
+    const size_t row_smem = ((size_t)CL_TILE * dp + (size_t)C * d) * sizeof(double);   // staged rows + transposed centroids
     if (row_smem > (size_t)200 * 1024) return fail(B200MNN_EINVAL, "internal: too many dimensions for the cluster plan");
 
     ClusterPlan& p = *plan;
@@ -405,6 +452,7 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     p.vref = ws.get<unsigned long long>((size_t)C * C);
     int32_t* cid_ref = ws.get<int32_t>((size_t)n);
     double* sample = ws.get<double>((size_t)m * d);
+    double* subset_t = ws.get<double>((size_t)mf * d);
     double* sums = ws.get<double>((size_t)C * d);
     double* cnorm = ws.get<double>((size_t)C);
     int* ints = ws.get<int>((size_t)8 * CL_MAXC + 16);
@@ -429,7 +477,9 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
 
     gather_sample_kernel<<<(unsigned)ceil_div((int64_t)m * d, 256), 256, 0, stream>>>(dX, n, d, m, sample);
     B200_LAUNCH_CHECK();
-    fps_seed_kernel<<<1, 1024, 0, stream>>>(sample, m, d, mf, C, p.centroids);
+    transpose_subset_kernel<<<(unsigned)ceil_div((int64_t)mf * d, 256), 256, 0, stream>>>(sample, m, d, mf, subset_t);
+    B200_LAUNCH_CHECK();
+    fps_seed_kernel<<<1, 1024, (size_t)d * sizeof(double), stream>>>(subset_t, d, mf, C, p.centroids);
     B200_LAUNCH_CHECK();
     for (int it = 0; it < LLOYD_ITERS; ++it) {
         centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
@@ -457,7 +507,7 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
 
     fill_vref_kernel<<<(unsigned)ceil_div((int64_t)C * C, 256), 256, 0, stream>>>(p.vref, C * C);
     B200_LAUNCH_CHECK();
-    tile_project_kernel<0><<<(unsigned)(p.n_rows_max / CL_TILE), 256, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids,
+    tile_project_kernel<0><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids,
                                                                                         p.cdist, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
     B200_TRY(build_tile_lists(p, dQ, d, p.qmap, p.nslots, p.nslots_max, qnorm, scale_exp, maxnorm_bits, p.cl_list, p.qoff, stream));
@@ -482,8 +532,8 @@ int build_tile_lists(const ClusterPlan& p, const double* dQ, int d, const int32_
                      const double* qnorm, const int* scale_exp, const unsigned long long* maxnorm_bits, int2* lists, float* qoff,
                      cudaStream_t stream) {
     const int dp = d | 1;
-    const size_t row_smem = (size_t)CL_TILE * dp * sizeof(double);
-    tile_project_kernel<1><<<(unsigned)(max_slots / CL_TILE), 256, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids, p.cdist,
+    const size_t row_smem = ((size_t)CL_TILE * dp + (size_t)p.C * d) * sizeof(double);
+    tile_project_kernel<1><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids, p.cdist,
                                                                                      p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
     B200_LAUNCH_CHECK();
     return 0;

@@ -890,6 +890,14 @@ __device__ __forceinline__ uint32_t ord_bits(float s) {
 __device__ __forceinline__ float ord_float(uint32_t u) { return __uint_as_float(u ^ (((u >> 31) - 1u) | 0x80000000u)); }
 constexpr uint32_t ORD_INF = 0xFF800000u;   // ord_bits(+inf)
 
+// Select that the compiler cannot turn back into a branch (the insertion rounds must stay straight-line code so that the
+// dependent chains of several rows interleave).
+__device__ __forceinline__ uint32_t sel_u32(const bool c, const uint32_t a, const uint32_t b) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)c));
+    return r;
+}
+
 // Stages one 32x32 chunk of scores (registers, lane = row) in shared memory, XOR-swizzled so that both these row-wise
 // writes and the column-wise reads of ts_chunk_score are bank-conflict free.
 __device__ __forceinline__ void ts_stage_chunk(const uint32_t (&v)[32], float4* __restrict__ stg, const int lane) {
@@ -986,12 +994,12 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
             for (int i = 0; i < NR; ++i) {
                 const bool doit = act[i] && sj[i] < curmax[i];
                 const bool in0 = doit && (E == 1 || b0[i] != 0u) && lane == __ffs(b0[i]) - 1;
-                e0[i].x = in0 ? sj[i] : e0[i].x;
-                e0[i].y = in0 ? idj[i] : e0[i].y;
+                e0[i].x = sel_u32(in0, sj[i], e0[i].x);
+                e0[i].y = sel_u32(in0, idj[i], e0[i].y);
                 if (E == 2) {
                     const bool in1 = doit && b0[i] == 0u && lane == __ffs(b1[i]) - 1;
-                    e1[i].x = in1 ? sj[i] : e1[i].x;
-                    e1[i].y = in1 ? idj[i] : e1[i].y;
+                    e1[i].x = sel_u32(in1, sj[i], e1[i].x);
+                    e1[i].y = sel_u32(in1, idj[i], e1[i].y);
                 }
             }
 #pragma unroll
@@ -1874,10 +1882,10 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     int nclusters = 64;
     if (const char* ce = getenv("B200MNN_CLUSTERS")) {
         const int c = atoi(ce);
-        if (c >= 8 && c <= CL_MAXC && (c & (c - 1)) == 0) nclusters = c;
+        if (c >= 16 && c <= CL_MAXC && (c & (c - 1)) == 0) nclusters = c;
     }
     const char* penv = getenv("B200MNN_PRUNE");
-    const bool prune_ok = use_ts && !dbg && n >= 8 * (int64_t)nclusters && (size_t)CL_TILE * (d | 1) * sizeof(double) <= (size_t)200 * 1024;
+    const bool prune_ok = use_ts && !dbg && n >= 8 * (int64_t)nclusters && ((size_t)CL_TILE * (d | 1) + (size_t)nclusters * d) * sizeof(double) <= (size_t)200 * 1024;
     const bool use_prune = prune_ok && (penv ? atoi(penv) == 1 : (n >= 65536 && nq >= 16384));
     const int64_t n_pad = use_prune ? round_up(n, CL_TILE) + (int64_t)nclusters * CL_TILE : round_up(n, bn);
     const int64_t nq_pad = round_up(nq, BM);

@@ -102,12 +102,12 @@ def test_query_knn_medium_against_kmknn_port():
 # Pruned search (csrc/knn_cluster.cu): forced on small inputs with few clusters; the answer must not change at all.
 @pytest.mark.parametrize("n,nq,d,k,ncomp,nclus", [
     (6000, 5000, 50, 20, 8, 16),
-    (4097, 129, 50, 1, 8, 8),        # ragged tiles, k = 1
+    (4097, 129, 50, 1, 8, 16),       # ragged tiles, k = 1
     (3000, 3000, 50, 30, 8, 16),     # 64-entry candidate lists
     (5000, 2000, 17, 7, 4, 32),      # more clusters than mixture components
-    (3000, 1000, 100, 10, 8, 8),
+    (3000, 1000, 100, 10, 8, 16),
     (2500, 4000, 3, 5, 2, 64),       # low dimension: bounds bite inside components too
-    (700, 300, 50, 20, 8, 8),        # barely enough rows for the clustering
+    (700, 300, 50, 20, 8, 16),       # barely enough rows for the clustering
 ])
 def test_query_knn_pruned_matches_oracle_bit_exact(n, nq, d, k, ncomp, nclus, monkeypatch):
     monkeypatch.setenv("B200MNN_PRUNE", "1")
@@ -122,7 +122,7 @@ def test_query_knn_pruned_matches_oracle_bit_exact(n, nq, d, k, ncomp, nclus, mo
 def test_query_knn_pruned_degenerate_inputs(monkeypatch):
     """Duplicates (coincident centroids), exact ties, unclustered data and far-apart blobs with the pruning forced on."""
     monkeypatch.setenv("B200MNN_PRUNE", "1")
-    monkeypatch.setenv("B200MNN_CLUSTERS", "8")
+    monkeypatch.setenv("B200MNN_CLUSTERS", "16")
     rng = np.random.default_rng(11)
     cases = []
     X = np.zeros((600, 50)); X[:, 0] = np.repeat(np.arange(12.0), 50)          # 50 exact duplicates per location
