@@ -165,12 +165,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Spin with a watchdog: a protocol bug must surface as a trapped kernel (-> CUDA error -> B200MNN_ECUDA),
 // never as a hung GPU.
+#ifndef B200_SPIN_BACKOFF
+#define B200_SPIN_BACKOFF 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
+        ++spins;
+        // long waits (the producer and the MMA issuers while the epilogue works through a hit-heavy tile) back off, so
+        // that the polling loop does not take issue slots from the epilogue warps of the same scheduler
+        if (B200_SPIN_BACKOFF && spins > 16u) __nanosleep(B200_SPIN_BACKOFF);
+        if ((spins & 0x3FFu) == 0 && clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
             printf("b200mnn: mbarrier watchdog fired (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y,
                    threadIdx.x, bar, parity);
             __trap();
@@ -187,7 +194,9 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-        if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
+        ++spins;
+        if (B200_SPIN_BACKOFF && spins > 16u) __nanosleep(B200_SPIN_BACKOFF);
+        if ((spins & 0x3FFu) == 0 && clock64() - t0 > 20000000000LL) {  // ~10 s at 2 GHz
             if ((threadIdx.x & 31) == 0)
                 printf("b200mnn: mbarrier watchdog fired (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
             __trap();
@@ -863,6 +872,8 @@ struct PruneArgs {
     const float* qoff;       // [slot] S^2 ||q||^2 rounded up, -inf for padding slots
     int C;
     unsigned long long* visited;   // optional counter: tiles scored by this launch
+    unsigned long long* mma_count; // optional counter (profiling): tcgen05.mma instructions issued = tiles x MMAs per tile
+    int mma_per_tile;
 };
 __device__ __forceinline__ void umma_f16_ts_impl(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -1166,6 +1177,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             for (int t = tile0; t < tile1; ++t) emit(t);
         }
         if (P.visited && lane == 0) atomicAdd(P.visited, (unsigned long long)seq);
+        if (P.mma_count && lane == 0) atomicAdd(P.mma_count, (unsigned long long)seq * (unsigned long long)P.mma_per_tile);
         emit(-1);
         emit(-1);
     } else if (warp == 1 || warp == 10) {
@@ -1591,8 +1603,32 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
             if (dbg_d2) dbg_d2[jq * ncand + c] = cd[r];
         }
     }
-    // k rounds of warp arg-min under (distance, index)
     double dk = INFINITY;
+    if (rounds == 1 && k <= 32) {
+        // One candidate per lane (the usual case): bitonic sort of the 32 (distance, index) pairs across the lanes, then
+        // lane j < k holds the j-th neighbour.
+        double sd = cd[0];
+        int si = (ci[0] >= 0) ? ci[0] : 0x7fffffff;   // empty slots sort last
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, sd, j);
+                const int oi = __shfl_xor_sync(0xffffffffu, si, j);
+                const bool up = (lane & kk) == 0, low = (lane & j) == 0;
+                const bool mine_first = pair_less(sd, si, od, oi);
+                const bool keep = (mine_first == (up == low));
+                sd = keep ? sd : od;
+                si = keep ? si : oi;
+            }
+        }
+        if (lane < k) {
+            out_idx[q * k + lane] = (si == 0x7fffffff) ? -1 : si;
+            if (out_dist) out_dist[q * k + lane] = sqrt(sd);
+        }
+        dk = __shfl_sync(0xffffffffu, sd, k - 1);
+    } else {
+    // k rounds of warp arg-min under (distance, index)
     for (int j = 0; j < k; ++j) {
         double bd = INFINITY;
         int bi = 0x7fffffff, br = -1;
@@ -1617,6 +1653,7 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
             if (out_dist) out_dist[q * k + j] = sqrt(wd);
         }
         dk = wd;
+    }
     }
     // certificate: every non-candidate j has score_j >= min_split thr, and |score_j/S^2 + ||q||^2 - d2_j| <= eps
     if (lane == 0) {
@@ -1813,6 +1850,7 @@ static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static double g_prof_flops = 0.0;
+static unsigned long long* g_prof_mma = nullptr;   // device counter of issued MMAs (TS kernel), allocated on first use
 
 int profile_enable(int on) {
     std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -1820,6 +1858,19 @@ int profile_enable(int on) {
     g_prof_events.clear();
     g_prof_flops = 0.0;
     g_prof_on = on != 0;
+    if (g_prof_on) {
+        if (!g_prof_mma) B200_CUDA(cudaMalloc(&g_prof_mma, sizeof(unsigned long long)));
+        B200_CUDA(cudaMemset(g_prof_mma, 0, sizeof(unsigned long long)));
+    }
+    return 0;
+}
+
+// Executed tensor-core work of the profiled launches: every tcgen05.mma of the TS kernel is M128 x N128 x K16.
+int profile_collect_executed(double* executed_flops) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    unsigned long long h = 0;
+    if (g_prof_mma) B200_CUDA(cudaMemcpy(&h, g_prof_mma, sizeof(h), cudaMemcpyDeviceToHost));
+    if (executed_flops) *executed_flops = (double)h * 2.0 * BM * TS_BN * SLICE;
     return 0;
 }
 
@@ -2104,11 +2155,17 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     };
 
     const bool fast_only_env = tenv && atoi(tenv) == 3;   // measurement aid: tier 1 only (uncertified queries go straight to the rescue)
-    PruneArgs prune1 = {nullptr, nullptr, nullptr, 0, visited};
-    PruneArgs prune2 = {nullptr, nullptr, nullptr, 0, visited + 1};
+    unsigned long long* mma_counter = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        if (g_prof_on) mma_counter = g_prof_mma;
+    }
+    auto mma_per_tile = [&](bool fast) { const MmaSched sc = make_sched(L, fast); int t = 0; for (int b = 0; b < sc.nbox; ++b) t += sc.nmma[b]; return t; };
+    PruneArgs prune1 = {nullptr, nullptr, nullptr, 0, visited, mma_counter, mma_per_tile(two_tier)};
+    PruneArgs prune2 = {nullptr, nullptr, nullptr, 0, visited + 1, mma_counter, mma_per_tile(false)};
     if (use_prune) {
-        prune1 = PruneArgs{plan.cl_list, plan.cl_tile0, plan.qoff, plan.C, visited};
-        prune2 = PruneArgs{lists2, plan.cl_tile0, qoff2, plan.C, visited + 1};
+        prune1 = PruneArgs{plan.cl_list, plan.cl_tile0, plan.qoff, plan.C, visited, mma_counter, mma_per_tile(two_tier)};
+        prune2 = PruneArgs{lists2, plan.cl_tile0, qoff2, plan.C, visited + 1, mma_counter, mma_per_tile(false)};
     }
     const int32_t* qmap1 = use_prune ? plan.qmap : nullptr;
     const int* qcount1 = use_prune ? plan.nslots : nullptr;
@@ -2176,6 +2233,8 @@ int b200mnn_profile_enable(int on) { return b200::knn::profile_enable(on); }
 int b200mnn_profile_collect(double* total_ms, int64_t* launches, double* algorithmic_flops) {
     return b200::knn::profile_collect(total_ms, launches, algorithmic_flops);
 }
+
+int b200mnn_profile_collect_executed(double* executed_flops) { return b200::knn::profile_collect_executed(executed_flops); }
 
 int b200mnn_dev_query_knn(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
                           int64_t* d_stats, void* stream) {

@@ -179,6 +179,9 @@ int b200mnn_dev_debug_candidates(const double* dX, int64_t n, const double* dQ, 
  * launch) they covered.  b200mnn_profile_enable(x) also clears earlier records. */
 int b200mnn_profile_enable(int on);
 int b200mnn_profile_collect(double* total_ms, int64_t* launches, double* algorithmic_flops);
+/* Tensor-core flops actually executed by the profiled launches (cluster pruning skips most score tiles; the second
+ * scoring tier adds some): issued tcgen05.mma instructions x 2*128*128*16. */
+int b200mnn_profile_collect_executed(double* executed_flops);
 
 #ifdef __cplusplus
 }
