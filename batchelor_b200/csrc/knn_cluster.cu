@@ -118,20 +118,25 @@ __global__ void __launch_bounds__(1024) fps_seed_kernel(const double* __restrict
 
 // Centroids transposed into shared memory ([t][c], c fastest) and the dot products of one row with 16 of them: per
 // dimension one row element and eight broadcast 16-byte loads feed sixteen FMAs.
-__device__ __forceinline__ void load_centroids_t(const double* __restrict__ cen, int C, int d, double* cenT) {
-    for (int e = threadIdx.x; e < C * d; e += blockDim.x) {
-        const int c = e / d, t = e - c * d;
-        cenT[t * C + c] = cen[e];
-    }
+__global__ void transpose_centroids_kernel(const double* __restrict__ cen, int C, int d, double* __restrict__ cenT_g) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= C * d) return;
+    const int t = e / C, c = e - t * C;
+    cenT_g[e] = cen[(size_t)c * d + t];
 }
-__device__ __forceinline__ void dots16(const double* __restrict__ x, int d, int C, const double* __restrict__ cenT, int c0, double (&a)[16]) {
+// cenT_g: the centroids already transposed ([t][c]) in global memory -> linear, conflict-free copy
+__device__ __forceinline__ void load_centroids_t(const double* __restrict__ cenT_g, int C, int d, double* cenT) {
+    for (int e = threadIdx.x; e < C * d; e += blockDim.x) cenT[e] = cenT_g[e];
+}
+template <int PASS>
+__device__ __forceinline__ void dots(const double* __restrict__ x, int d, int C, const double* __restrict__ cenT, int c0, double (&a)[PASS]) {
 #pragma unroll
-    for (int u = 0; u < 16; ++u) a[u] = 0.0;
+    for (int u = 0; u < PASS; ++u) a[u] = 0.0;
     for (int t = 0; t < d; ++t) {
         const double xv = x[t];
         const double2* cp = reinterpret_cast<const double2*>(cenT + t * C + c0);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < PASS / 2; ++u) {
             const double2 cv = cp[u];
             a[2 * u] = fma(xv, cv.x, a[2 * u]);
             a[2 * u + 1] = fma(xv, cv.y, a[2 * u + 1]);
@@ -139,16 +144,18 @@ __device__ __forceinline__ void dots16(const double* __restrict__ x, int d, int 
     }
 }
 
-// Nearest centroid of one row held in shared memory (C is a multiple of 16).
+// Nearest centroid of one row (C is a multiple of PASS).  With PASS = 64 the row is read once per 64 centroids and
+// the loop is FMA-bound (one row element + 32 broadcast 16-byte loads feed 64 FMAs).
+template <int PASS>
 __device__ __forceinline__ int nearest_centroid(const double* __restrict__ x, int d, int C, const double* __restrict__ cenT,
                                                 const double* __restrict__ cnorm) {
     double best = INFINITY;
     int bi = 0;
-    for (int c0 = 0; c0 < C; c0 += 16) {
-        double a[16];
-        dots16(x, d, C, cenT, c0, a);
+    for (int c0 = 0; c0 < C; c0 += PASS) {
+        double a[PASS];
+        dots<PASS>(x, d, C, cenT, c0, a);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < PASS; ++u) {
             const double sc = cnorm[c0 + u] - 2.0 * a[u];
             if (sc < best) { best = sc; bi = c0 + u; }
         }
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(CL_TILE) lloyd_accum_kernel(const double* __re
     const int64_t i = row0 + threadIdx.x;
     if (i >= m) return;
     const double* x = rows + threadIdx.x * dp;
-    const int c = nearest_centroid(x, d, C, cenT, cnorm);
+    const int c = nearest_centroid<16>(x, d, C, cenT, cnorm);
     for (int t = 0; t < d; ++t) atomicAdd(sums + (size_t)c * d + t, x[t]);
     atomicAdd(counts + c, 1);
 }
@@ -202,32 +209,33 @@ __global__ void lloyd_update_kernel(double* __restrict__ cen, int C, int d, doub
     if (threadIdx.x == 0) counts[c] = 0;
 }
 
-__global__ void centroid_dist_kernel(const double* __restrict__ cen, int C, int d, double* __restrict__ cdist) {
+// cdist[a][b] = |c_a - c_b| and its reciprocal (the projection kernels multiply; the rounding is inside their margin)
+__global__ void centroid_dist_kernel(const double* __restrict__ cen, int C, int d, double* __restrict__ cdist, double* __restrict__ cinv) {
     const int a = blockIdx.x;
     for (int b = threadIdx.x; b < C; b += blockDim.x) {
         double s = 0.0;
         for (int t = 0; t < d; ++t) { const double df = cen[(size_t)a * d + t] - cen[(size_t)b * d + t]; s = fma(df, df, s); }
-        cdist[(size_t)a * C + b] = sqrt(s);
+        const double D = sqrt(s);
+        cdist[(size_t)a * C + b] = D;
+        cinv[(size_t)a * C + b] = D > 0.0 ? 1.0 / D : 0.0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Assignment of every row, grouping
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restrict__ X, int64_t n, int d, int dp, int C,
+template <int PASS>
+__global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restrict__ X, int64_t n, int d, int C,
                                                        const double* __restrict__ cen, const double* __restrict__ cnorm,
                                                        int32_t* __restrict__ cid, int* __restrict__ counts) {
-    extern __shared__ double rows[];
-    double* cenT = rows + CL_TILE * dp;
-    const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
-    stage_rows(X, row0, n, d, dp, rows);
+    extern __shared__ double cenT[];   // [d][C]
     load_centroids_t(cen, C, d, cenT);
     __syncthreads();
-    const int64_t i = row0 + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * CL_TILE + threadIdx.x;
     const bool valid = i < n;
     int c = -1;
     if (valid) {
-        c = nearest_centroid(rows + threadIdx.x * dp, d, C, cenT, cnorm);
+        c = nearest_centroid<PASS>(X + i * d, d, C, cenT, cnorm);   // a warp's 32 rows are contiguous: L1 serves the strided reads
         cid[i] = c;
     }
     // warp-aggregated histogram
@@ -270,15 +278,15 @@ __global__ void scatter_kernel(const int32_t* __restrict__ cid, int64_t n, const
 // ---------------------------------------------------------------------------------------------------------------
 // Projections of a tile's rows on the centroid axes
 // ---------------------------------------------------------------------------------------------------------------
-// Block = 128 threads, one row each, every cluster in passes of 16 (dots16).
+// Block = 128 threads, one row each, every cluster in passes of PASS (dots).
 // MODE 0 (reference tile): vref[P][c] = max over rows of (x.c_c - x.c_P) / D(P,c) + margin   (P = the tile's cluster)
 // MODE 1 (query tile)    : LB[c] = min over rows of -ext_c(P_r) - (q.c_c - q.c_P_r) / D(P_r,c) - margin, then the sorted
 //                          cluster list and the per-slot score offsets.
-template <int MODE>
+template <int MODE, int PASS>
 __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __restrict__ X, int d, int dp, int C, const int32_t* __restrict__ map,
                                                              const int* __restrict__ count, const int32_t* __restrict__ cid,
                                                              const double* __restrict__ cen, const double* __restrict__ cdist,
-                                                             unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
+                                                             const double* __restrict__ cinv, unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
                                                              const double* __restrict__ qnorm, const int* __restrict__ scale_exp,
                                                              int2* __restrict__ lists, float* __restrict__ qoff) {
     extern __shared__ double rows[];                 // [128][dp] rows, then [d][C] transposed centroids
@@ -292,9 +300,20 @@ __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __r
     for (int c = tid; c < CL_MAXC; c += CL_TILE) red[c] = (MODE == 0) ? dkey(-INFINITY) : dkey(INFINITY);
     __syncthreads();
     if (MODE == 0 && src_s[0] < 0) return;           // clusters are padded at their end: an empty first row = an unused tile
-    for (int r = warp; r < CL_TILE; r += CL_TILE / 32) {
-        const int64_t s = src_s[r];
-        for (int t = lane; t < d; t += 32) rows[r * dp + t] = (s >= 0) ? X[s * d + t] : 0.0;
+    for (int t0 = 0; t0 < d; t0 += 32) {   // gathered rows: eight independent loads in flight per lane
+        const int t = t0 + lane;
+#pragma unroll 1
+        for (int rb = warp * 32; rb < warp * 32 + 32; rb += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t s = src_s[rb + u];
+                v[u] = (s >= 0 && t < d) ? X[s * d + t] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (t < d) rows[(rb + u) * dp + t] = v[u];
+        }
     }
     load_centroids_t(cen, C, d, cenT);
     __syncthreads();
@@ -305,19 +324,20 @@ __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __r
     const double M = sqrt(__longlong_as_double((long long)*maxnorm_bits));
     double gP = 0.0, xn = 0.0;
     for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, cenT[t * C + P], gP); xn = fma(xv, xv, xn); }
-    const double mg_num = 1e-11 * (sqrt(xn) + M) * M;   // >= 1000x the rounding error of the two dot products
+    const double mg_num = 1e-11 * (sqrt(xn) + M) * M;   // >= 1000x the rounding error of the two dot products and the reciprocal
     const double tiny = 1e-5 * M;
-    for (int c0 = 0; c0 < C; c0 += 16) {
-        double a[16];
-        dots16(x, d, C, cenT, c0, a);
+    for (int c0 = 0; c0 < C; c0 += PASS) {
+        double a[PASS];
+        dots<PASS>(x, d, C, cenT, c0, a);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < PASS; ++u) {
             const int c = c0 + u;
             const double D = cdist[(size_t)P * C + c];
+            const double iD = cinv[(size_t)P * C + c];
             double val;
             if (MODE == 0) {
                 // extent of this row towards centroid c, rounded up; coincident centroids give no usable axis
-                val = (valid && c != P) ? ((D > tiny) ? (a[u] - gP) / D + mg_num / D : INFINITY) : -INFINITY;
+                val = (valid && c != P) ? ((D > tiny) ? (a[u] - gP + mg_num) * iD : INFINITY) : -INFINITY;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) val = fmax(val, __shfl_xor_sync(0xffffffffu, val, o));
                 if (lane == 0) atomicMax(&red[c], dkey(val));
@@ -326,7 +346,7 @@ __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __r
                 else if (c == P || !(D > tiny)) val = -INFINITY;
                 else {
                     const double ext = dkey_inv(vref[(size_t)c * C + P]);   // -inf for an empty cluster -> LB = +inf
-                    val = -ext - (a[u] - gP) / D - mg_num / D;
+                    val = -ext - (a[u] - gP + mg_num) * iD;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, o));
@@ -449,6 +469,8 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     p.cid_q = ws.get<int32_t>((size_t)nq);
     p.centroids = ws.get<double>((size_t)C * d);
     p.cdist = ws.get<double>((size_t)C * C);
+    p.cinv = ws.get<double>((size_t)C * C);
+    p.centroids_t = ws.get<double>((size_t)C * d);
     p.vref = ws.get<unsigned long long>((size_t)C * C);
     int32_t* cid_ref = ws.get<int32_t>((size_t)n);
     double* sample = ws.get<double>((size_t)m * d);
@@ -470,10 +492,14 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     B200_CUDA(cudaMemsetAsync(p.refmap, 0xFF, sizeof(int32_t) * (size_t)p.n_rows_max, stream));
     B200_CUDA(cudaMemsetAsync(p.qmap, 0xFF, sizeof(int32_t) * (size_t)p.nslots_max, stream));
 
+    const size_t cen_smem = (size_t)C * d * sizeof(double);
     B200_TRY(set_smem((const void*)lloyd_accum_kernel, row_smem));
-    B200_TRY(set_smem((const void*)assign_kernel, row_smem));
-    B200_TRY(set_smem((const void*)tile_project_kernel<0>, row_smem));
-    B200_TRY(set_smem((const void*)tile_project_kernel<1>, row_smem));
+    B200_TRY(set_smem((const void*)assign_kernel<16>, cen_smem));
+    B200_TRY(set_smem((const void*)assign_kernel<64>, cen_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<0, 16>, row_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<1, 16>, row_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<0, 64>, row_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<1, 64>, row_smem));
 
     gather_sample_kernel<<<(unsigned)ceil_div((int64_t)m * d, 256), 256, 0, stream>>>(dX, n, d, m, sample);
     B200_LAUNCH_CHECK();
@@ -484,20 +510,31 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     for (int it = 0; it < LLOYD_ITERS; ++it) {
         centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
         B200_LAUNCH_CHECK();
-        lloyd_accum_kernel<<<(unsigned)ceil_div(m, CL_TILE), CL_TILE, row_smem, stream>>>(sample, m, d, dp, C, p.centroids, cnorm, sums, counts);
+        transpose_centroids_kernel<<<(unsigned)ceil_div((int64_t)C * d, 256), 256, 0, stream>>>(p.centroids, C, d, p.centroids_t);
+        B200_LAUNCH_CHECK();
+        lloyd_accum_kernel<<<(unsigned)ceil_div(m, CL_TILE), CL_TILE, row_smem, stream>>>(sample, m, d, dp, C, p.centroids_t, cnorm, sums, counts);
         B200_LAUNCH_CHECK();
         lloyd_update_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, sums, counts);
         B200_LAUNCH_CHECK();
     }
     centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
     B200_LAUNCH_CHECK();
-    centroid_dist_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, p.cdist);
+    centroid_dist_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, p.cdist, p.cinv);
+    B200_LAUNCH_CHECK();
+    transpose_centroids_kernel<<<(unsigned)ceil_div((int64_t)C * d, 256), 256, 0, stream>>>(p.centroids, C, d, p.centroids_t);
     B200_LAUNCH_CHECK();
 
-    assign_kernel<<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, row_smem, stream>>>(dX, n, d, dp, C, p.centroids, cnorm, cid_ref, cnt_ref);
-    B200_LAUNCH_CHECK();
-    assign_kernel<<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, row_smem, stream>>>(dQ, nq, d, dp, C, p.centroids, cnorm, p.cid_q, cnt_q);
-    B200_LAUNCH_CHECK();
+    if (C % 64 == 0) {
+        assign_kernel<64><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, cnorm, cid_ref, cnt_ref);
+        B200_LAUNCH_CHECK();
+        assign_kernel<64><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, cnorm, p.cid_q, cnt_q);
+        B200_LAUNCH_CHECK();
+    } else {
+        assign_kernel<16><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, cnorm, cid_ref, cnt_ref);
+        B200_LAUNCH_CHECK();
+        assign_kernel<16><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, cnorm, p.cid_q, cnt_q);
+        B200_LAUNCH_CHECK();
+    }
     offsets_kernel<<<1, 256, 0, stream>>>(cnt_ref, cnt_q, C, p.cl_tile0, row_base, slot_base, p.nslots, cursors);
     B200_LAUNCH_CHECK();
     scatter_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cid_ref, n, row_base, cursors, p.refmap);
@@ -507,8 +544,12 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
 
     fill_vref_kernel<<<(unsigned)ceil_div((int64_t)C * C, 256), 256, 0, stream>>>(p.vref, C * C);
     B200_LAUNCH_CHECK();
-    tile_project_kernel<0><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids,
-                                                                                        p.cdist, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
+    if (C % 64 == 0)
+        tile_project_kernel<0, 64><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
+                                                                                                p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
+    else
+        tile_project_kernel<0, 16><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
+                                                                                                p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
     B200_TRY(build_tile_lists(p, dQ, d, p.qmap, p.nslots, p.nslots_max, qnorm, scale_exp, maxnorm_bits, p.cl_list, p.qoff, stream));
     return 0;
@@ -533,8 +574,12 @@ int build_tile_lists(const ClusterPlan& p, const double* dQ, int d, const int32_
                      cudaStream_t stream) {
     const int dp = d | 1;
     const size_t row_smem = ((size_t)CL_TILE * dp + (size_t)p.C * d) * sizeof(double);
-    tile_project_kernel<1><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids, p.cdist,
-                                                                                     p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
+    if (p.C % 64 == 0)
+        tile_project_kernel<1, 64><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids_t, p.cdist,
+                                                                                             p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
+    else
+        tile_project_kernel<1, 16><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids_t, p.cdist,
+                                                                                             p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -25,7 +25,9 @@ struct ClusterPlan {
     float* qoff = nullptr;       // [nslots_max]  S^2 ||q||^2 rounded up (-inf for padding slots)
     int32_t* cid_q = nullptr;    // [nq] cluster of every query (original order)
     double* centroids = nullptr; // [C][d]
+    double* centroids_t = nullptr;   // [d][C] the same, transposed (what the kernels stage in shared memory)
     double* cdist = nullptr;     // [C][C] centroid distances
+    double* cinv = nullptr;      // [C][C] their reciprocals
     unsigned long long* vref = nullptr;   // [C][C] ordered-key maxima: extent of cluster B's rows towards centroid A
 };
 
