@@ -941,6 +941,15 @@ __device__ __forceinline__ void ts_fill_staged(const int col0, const int seg, ui
 #ifndef B200_INS_ROWS
 #define B200_INS_ROWS 4
 #endif
+#ifndef B200_OPT_CLZ
+#define B200_OPT_CLZ 1
+#endif
+#ifndef B200_OPT_HOLDER
+#define B200_OPT_HOLDER 1
+#endif
+#ifndef B200_OPT_MASK
+#define B200_OPT_MASK 0
+#endif
 template <int E>
 __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, float& thr, uint2* __restrict__ list,
                                                  volatile float* __restrict__ thr_pub, const float4* __restrict__ stg, const int lane, long long* stat) {
@@ -959,8 +968,13 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
         float thrL[NR], sc[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
+#if B200_OPT_CLZ
+            L[i] = 31 - __clz(hit);                      // highest hitting row first (FLO; ffs would need BREV + FLO); -1: slot unused,
+            hit &= ~((L[i] >= 0 ? 1u : 0u) << (L[i] & 31));   // rides along on row L[0], never stored
+#else
             L[i] = hit ? __ffs(hit) - 1 : -1;            // -1: slot unused (rides along on row L[0], never stored)
             hit &= hit - 1;
+#endif
         }
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
@@ -990,8 +1004,13 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 act[i] = m[i] != 0u;
+#if B200_OPT_CLZ
+                const int j = act[i] ? 31 - __clz(m[i]) : 0;   // any order of the row's hits will do
+                m[i] &= ~((act[i] ? 1u : 0u) << j);
+#else
                 const int j = act[i] ? __ffs(m[i]) - 1 : 0;
                 m[i] &= m[i] - 1u;
+#endif
                 any |= m[i];
                 idj[i] = (uint32_t)(col0 + j);
                 sj[i] = __shfl_sync(0xffffffffu, so[i], j);
@@ -1004,11 +1023,27 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 const bool doit = act[i] && sj[i] < curmax[i];
+                // any holder of the maximum will do: the highest such lane.  Bit-mask selects: the compiler cannot turn them
+                // back into branches (the rounds must stay straight-line code so that the rows' chains interleave).
+#if B200_OPT_HOLDER
+                const bool in0 = doit && (E == 1 || b0[i] != 0u) && lane == 31 - __clz(b0[i]);
+#else
                 const bool in0 = doit && (E == 1 || b0[i] != 0u) && lane == __ffs(b0[i]) - 1;
+#endif
+#if B200_OPT_MASK
+                const uint32_t k0 = in0 ? 0xffffffffu : 0u;
+                e0[i].x = (sj[i] & k0) | (e0[i].x & ~k0);
+                e0[i].y = (idj[i] & k0) | (e0[i].y & ~k0);
+#else
                 e0[i].x = sel_u32(in0, sj[i], e0[i].x);
                 e0[i].y = sel_u32(in0, idj[i], e0[i].y);
+#endif
                 if (E == 2) {
+#if B200_OPT_HOLDER
+                    const bool in1 = doit && b0[i] == 0u && lane == 31 - __clz(b1[i]);
+#else
                     const bool in1 = doit && b0[i] == 0u && lane == __ffs(b1[i]) - 1;
+#endif
                     e1[i].x = sel_u32(in1, sj[i], e1[i].x);
                     e1[i].y = sel_u32(in1, idj[i], e1[i].y);
                 }
