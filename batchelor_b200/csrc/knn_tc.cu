@@ -294,6 +294,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// 16 lanes x (2 x 32) consecutive fp32 columns: thread i < 16 receives columns [col, col+32) of lane base+i, thread
+// i >= 16 columns [col+32, col+64) of lane base+(i-16) (cute: SM100_TMEM_LOAD_16dp32b32x).  Lets the two epilogue warps
+// of a TMEM lane quarter split its ROWS (16 each) instead of the columns.
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x32bx2.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32], 32;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64).
 // Rows are 128 B apart, 8-row groups 1024 B apart (dense [rows][128 B] tile as written by TMA).
@@ -924,13 +940,17 @@ __device__ __forceinline__ float ts_chunk_score(const float4* __restrict__ stg, 
     return reinterpret_cast<const float*>(stg)[((g * 32 + (L ^ g)) << 2) + (lane & 3)];
 }
 // First chunks of a warp: copied straight into segment `seg` of every row's list (no selection needed yet).
-template <int KEEP>
-__device__ __forceinline__ void ts_fill_staged(const int col0, const int seg, uint2* __restrict__ list, const float4* __restrict__ stg, const int lane) {
+// First load of a warp: the staged values go straight into the lists (no selection needed yet).  Holder lane h < 16
+// carries columns [col0, col0+32) of row h, holder lane h + 16 columns [col0+32, col0+64) of the same row: the former
+// fill segment 0 of every list, the latter segment 1 when the lists have one (E == 2).
+template <int E>
+__device__ __forceinline__ void ts_fill_staged(const int col0, uint2* __restrict__ list, const float4* __restrict__ stg, const int lane) {
+    constexpr int KEEP = 32 * E;
 #pragma unroll 8
-    for (int L = 0; L < 32; ++L) {
-        const float sc = ts_chunk_score(stg, L, lane);
+    for (int H = 0; H < 16 * E; ++H) {
+        const float sc = ts_chunk_score(stg, H, lane);
         const uint32_t o = ord_bits(sc);
-        list[L * KEEP + seg * 32 + lane] = make_uint2(o, o >= ORD_INF ? 0xFFFFFFFFu : (uint32_t)(col0 + lane));   // padding rows score +inf
+        list[(H & 15) * KEEP + (H >> 4) * 32 + lane] = make_uint2(o, o >= ORD_INF ? 0xFFFFFFFFu : (uint32_t)(col0 + (H >> 4) * 32 + lane));   // padding rows score +inf
     }
     __syncwarp();
 }
@@ -981,9 +1001,9 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
             const int LL = L[i] < 0 ? L[0] : L[i];
             thrL[i] = __shfl_sync(0xffffffffu, thr, LL);
             sc[i] = ts_chunk_score(stg, LL, lane);
-            e0[i] = list[LL * KEEP + lane];
+            e0[i] = list[(LL & 15) * KEEP + lane];      // holder lane LL carries 32 columns of row LL & 15
             e1[i] = make_uint2(0u, 0u);
-            if (E == 2) e1[i] = list[LL * KEEP + 32 + lane];
+            if (E == 2) e1[i] = list[(LL & 15) * KEEP + 32 + lane];
         }
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
@@ -1012,7 +1032,7 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
                 m[i] &= m[i] - 1u;
 #endif
                 any |= m[i];
-                idj[i] = (uint32_t)(col0 + j);
+                idj[i] = (uint32_t)(col0 + ((L[i] >> 4) & 1) * 32 + j);
                 sj[i] = __shfl_sync(0xffffffffu, so[i], j);
             }
 #pragma unroll
@@ -1056,12 +1076,10 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             if (L[i] >= 0) {   // warp-uniform
-                list[L[i] * KEEP + lane] = e0[i];
-                if (E == 2) list[L[i] * KEEP + 32 + lane] = e1[i];
-                if (lane == L[i]) {
-                    thr = ord_float(curmax[i]);
-                    thr_pub[L[i]] = thr;
-                }
+                list[(L[i] & 15) * KEEP + lane] = e0[i];
+                if (E == 2) list[(L[i] & 15) * KEEP + 32 + lane] = e1[i];
+                if ((lane & 15) == (L[i] & 15)) thr = ord_float(curmax[i]);   // both holder lanes of the row
+                if (lane == L[i]) thr_pub[L[i] & 15] = ord_float(curmax[i]);
             }
         }
         if (stat) stat[7] += clock64() - tc3;
@@ -1100,11 +1118,11 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     constexpr int KEEP = 32 * E;
 
     uint8_t* smB = smem;
-    uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);                             // [8 warps][32 rows][KEEP] (score bits, id)
-    float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 32 * KEEP);                   // [8 warps][8][32]
-    float* thr_s = reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                                // [2 column halves][128] thresholds
-    volatile int* ring = reinterpret_cast<int*>(thr_s + 2 * BM);                                               // [TS_RING] tile ids, -1 = end
-    float* qoff_s = reinterpret_cast<float*>(thr_s + 2 * BM) + TS_RING;                                        // [128]
+    uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);                             // [8 warps][16 rows][KEEP] (score bits, id)
+    float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 16 * KEEP);                   // [8 warps][8][32]
+    float* thr_s = reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                                // [128] row thresholds
+    volatile int* ring = reinterpret_cast<int*>(thr_s + BM);                                                   // [TS_RING] tile ids, -1 = end
+    float* qoff_s = reinterpret_cast<float*>(thr_s + BM) + TS_RING;                                            // [128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + BM);
     uint64_t* full = bars;                     // [MAX_SLOTS]
     uint64_t* empty = bars + MAX_SLOTS;        // [MAX_SLOTS]
@@ -1139,7 +1157,6 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     }
     if (threadIdx.x < BM) {
         thr_s[threadIdx.x] = __int_as_float(0x7f800000);
-        thr_s[BM + threadIdx.x] = __int_as_float(0x7f800000);
         qoff_s[threadIdx.x] = (P.cl_list && (int64_t)m0 + threadIdx.x < nq_eff) ? P.qoff[m0 + threadIdx.x] : __int_as_float(0xff800000);
     }
     if (warp == 1) {
@@ -1199,7 +1216,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
 #pragma unroll
                         for (int r = lane; r < BM; r += 32) {
                             const float qo = qoff_s[r];
-                            if (qo > __int_as_float(0xff800000)) m = fmaxf(m, __fadd_ru(fminf(thr_v[r], thr_v[BM + r]), qo));
+                            if (qo > __int_as_float(0xff800000)) m = fmaxf(m, __fadd_ru(thr_v[r], qo));
                         }
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -1270,22 +1287,26 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         }
     } else {
         // ===================== epilogue: warps 2..9 =====================
-        const int grp = (warp - 2) >> 2;          // 0: columns 0..63 of every tile, 1: columns 64..127
-        const int pr = (warp - 2) & 3;            // pair: warps pr+2 and pr+6 read the same 32 TMEM lanes (query rows)
-        const int q4 = warp & 3;                  // TMEM lane quarter both warps of the pair may access
-        const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-        uint2* mylist = lists + (size_t)(warp - 2) * 32 * KEEP;                      // this warp's own candidate lists
+        // Two warps per TMEM lane quarter, 16 query rows each, all 128 columns of every tile: every row has ONE candidate
+        // list and one owner, so nothing is shared between warps.  tcgen05.ld 16x32bx2 hands thread t < 16 the columns
+        // [c, c+32) of row t and thread t + 16 the columns [c+32, c+64) of the same row; two such loads cover a tile.
+        const int grp = (warp - 2) >> 2;          // 0: rows 0..15 of the quarter, 1: rows 16..31
+        const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
+        const int row0 = q4 * 32 + grp * 16;      // first of this warp's 16 rows (CTA-relative)
+        const int half = lane >> 4;               // which 32-column half of a load this thread holds
+        uint2* mylist = lists + (size_t)(warp - 2) * 16 * KEEP;                      // this warp's candidate lists
         float4* stg = stage_all + (size_t)(warp - 2) * 8 * 32;
-        volatile float* thr_pub = thr_s + grp * BM + q4 * 32;                        // read by the producer's stop test
-        const uint32_t lane_acc = acc_base + lane_sel;
+        volatile float* thr_pub = thr_s + row0;                                      // read by the producer's stop test
+        const uint32_t lane_acc = acc_base + ((uint32_t)row0 << 16);
         long long acc_t[4] = {0, 0, 0, 0};   // measurement aid (trace only): tfull wait, TMEM load, scan + hits
-        long long stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // measurement aid (trace only), see ts_insert_hits
+        long long stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // measurement aid (trace only), see ts_insert_staged
         uint32_t v0[32], v1[32];
 #pragma unroll
-        for (int i = 0; i < KEEP; ++i) mylist[i * 32 + lane] = make_uint2(ORD_INF, 0xFFFFFFFFu);   // empty lists: score +inf, id -1
+        for (int i = 0; i < KEEP / 2; ++i) mylist[i * 32 + lane] = make_uint2(ORD_INF, 0xFFFFFFFFu);   // empty lists: score +inf, id -1
 
         if (grp == 0) {
-            // this thread's query row -> TMEM (A operand of every MMA of this CTA)
+            // this thread's query row -> TMEM (A operand of every MMA of this CTA); the warp covers the whole lane quarter
+            const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
             const int64_t j = (int64_t)m0 + q4 * 32 + lane;
             int64_t src = j;                                       // rows past nq are zero padding of opA
             if (qmap) src = (j < nq_eff) ? (int64_t)qmap[j] : -1;
@@ -1304,14 +1325,12 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         __syncwarp();
 
         // Tiles arrive in the producer's order; entry seq of the tile-id ring names the tile in accumulator stage
-        // seq % TS_STAGES (-1: end of the stream).  Per tile this warp scans 64 columns.  Quiet chunks (no score below
-        // any threshold of the warp's rows -- the common case of a dense scan) stay a short dependent chain: wait, two
-        // TMEM loads, release, two min trees, ONE vote.
+        // seq % TS_STAGES (-1: end of the stream).  Quiet tiles (no score below any threshold of the warp's rows -- the
+        // common case of a dense scan) stay a short dependent chain: wait, two TMEM loads, release, two min trees, ONE vote.
         int seq = 0, stage = 0;
         uint32_t par = 0;
-        int filled = 0;                                 // chunks copied straight into the lists (the first E)
-        float fillmax = __int_as_float(0xff800000);
-        float thr = __int_as_float(0x7f800000);         // == max of this lane's row list once the list is full
+        bool filled = false;                            // the first load of the stream went straight into the lists
+        float thr = __int_as_float(0x7f800000);         // threshold of row (lane & 15) == max of its list once that is full
         const bool skip_read = dbg_mode == 1;
         while (true) {
             long long c0 = 0, c1 = 0, c2 = 0;
@@ -1322,9 +1341,9 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             if (tile < 0) break;
             if (trace) c1 = clock64();
             if (!skip_read) {
-                const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN + grp * 64);
-                tmem_ld32(tbase, v0);
-                tmem_ld32(tbase + 32u, v1);
+                const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
+                tmem_ld16x2(tbase, v0);
+                tmem_ld16x2(tbase + 64u, v1);
                 tmem_ld_wait();
             }
             tc_fence_before();
@@ -1334,61 +1353,66 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             ++seq;
             if (trace) c2 = clock64();
             if (skip_read) continue;
-            const int col0 = tile * TS_BN + grp * 64;
+            const int col0 = tile * TS_BN;
             const float ma = chunk_min(v0), mb = chunk_min(v1);
-            if (filled == E && !__any_sync(0xffffffffu, fminf(ma, mb) < thr)) continue;   // quiet tile
-            // ONE copy of the fill / insertion code for both chunks (the loop is not unrolled): the hit path is long, and
-            // with a copy per call site the eight epilogue warps thrashed the instruction cache (IPC 0.2).
+            if (filled && !__any_sync(0xffffffffu, fminf(ma, mb) < thr)) continue;   // quiet tile
+            // ONE copy of the fill / insertion code for both loads (the loop is not unrolled): the hit path is long, and
+            // with a copy per call site the eight epilogue warps thrashed the instruction cache.
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
-                if (filled < E) {   // warp-uniform: the first E chunks of this warp go straight into the lists
-                    float mx;
-                    if (c == 0) { ts_stage_chunk(v0, stg, lane); mx = chunk_max(v0); }
-                    else { ts_stage_chunk(v1, stg, lane); mx = chunk_max(v1); }
-                    ts_fill_staged<KEEP>(col0 + 32 * c, filled, mylist, stg, lane);
-                    fillmax = fmaxf(fillmax, mx);
-                    if (++filled == E) { thr = (dbg_mode == 8) ? __int_as_float(0xff800000) : fillmax; thr_pub[lane] = thr; }
+                unsigned h;
+                if (!filled) {   // warp-uniform: the very first load of this warp
+                    ts_stage_chunk(v0, stg, lane);
+                    ts_fill_staged<E>(col0, mylist, stg, lane);
+                    // E == 1: the lists hold the first 32 columns; the other 32 are ordinary hits.  E == 2: all 64 are in.
+                    float mx = chunk_max(v0);
+                    if (E == 2) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                    else mx = __shfl_sync(0xffffffffu, mx, lane & 15);
+                    thr = (dbg_mode == 8) ? __int_as_float(0xff800000) : mx;
+                    if (lane < 16) thr_pub[lane] = thr;
+                    filled = true;
+                    if (E == 2) continue;
+                    h = __ballot_sync(0xffffffffu, ma < thr) & 0xffff0000u;
+                    if (h) ts_insert_staged<E>(h, col0, thr, mylist, thr_pub, stg, lane, trace ? stat : nullptr);
                     continue;
                 }
-                const unsigned h = __ballot_sync(0xffffffffu, (c == 0 ? ma : mb) < thr);   // thr may just have tightened
+                h = __ballot_sync(0xffffffffu, (c == 0 ? ma : mb) < thr);   // thr may just have tightened
                 if (h == 0u) continue;
                 if (c == 0) ts_stage_chunk(v0, stg, lane);
                 else ts_stage_chunk(v1, stg, lane);
-                ts_insert_staged<E>(h, col0 + 32 * c, thr, mylist, thr_pub, stg, lane, trace ? stat : nullptr);
+                // the two holder lanes of a row must not be merged side by side: first the left 32 columns, then the right
+                if (h & 0x0000ffffu) ts_insert_staged<E>(h & 0x0000ffffu, col0 + 64 * c, thr, mylist, thr_pub, stg, lane, trace ? stat : nullptr);
+                h = __ballot_sync(0xffffffffu, (c == 0 ? ma : mb) < thr) & 0xffff0000u;
+                if (h) ts_insert_staged<E>(h, col0 + 64 * c, thr, mylist, thr_pub, stg, lane, trace ? stat : nullptr);
             }
             if (trace) { acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; acc_t[2] += clock64() - c2; }
         }
         __syncwarp();
-        pair_barrier(1 + pr);   // both lists of every row of the pair are final
         if (trace && lane == 0) {
             for (int i = 0; i < 4; ++i) dbg_ts[(warp - 2) * 8 + i] = acc_t[i];
             for (int i = 0; i < 3; ++i) dbg_ts[(warp - 2) * 8 + 4 + i] = stat[i];
             dbg_ts[(warp - 2) * 8 + 7] = seq;
             for (int i = 0; i < 7; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = stat[3 + i];
         }
-        // Output: the two warps of a pair merge and write 16 rows each.  The KEEP best of the union of both lists are the
-        // row's candidates and the KEEP-th best score its threshold: a rejected or evicted score was >= the list maximum
-        // of the warp that saw it, which only ever decreases and ends >= that KEEP-th best score.
-        const uint2* listA = lists + (size_t)pr * 32 * KEEP;
-        const uint2* listB = lists + (size_t)(pr + 4) * 32 * KEEP;
-        const int64_t rowbase = (int64_t)m0 + q4 * 32;
+        // Output: every warp sorts and writes its 16 rows.  The KEEP-th best score is the row's threshold: a rejected or
+        // evicted score was >= the list maximum at that time, which only ever decreases.
+        const int64_t rowbase = (int64_t)m0 + row0;
         const int64_t sbase = (int64_t)blockIdx.y * nq;
 #pragma unroll 1
-        for (int r = grp * 16; r < grp * 16 + 16; ++r) {
+        for (int r = 0; r < 16; ++r) {
             const int64_t row = rowbase + r;
             if (row >= nq_eff) break;   // warp-uniform
             unsigned long long a0[1], a1[1], pk[1];
-            uint2 t = listA[r * KEEP + lane];
+            uint2 t = mylist[r * KEEP + lane];
             a0[0] = ((unsigned long long)t.x << 32) | t.y;
             a1[0] = EMPTY_KEY;
-            if (E == 2) { t = listA[r * KEEP + 32 + lane]; a1[0] = ((unsigned long long)t.x << 32) | t.y; }
-            t = listB[r * KEEP + lane];
-            pk[0] = ((unsigned long long)t.x << 32) | t.y;
-            merge_keys<E, 1>(a0, a1, pk, true, lane);
-            if (E == 2) {
-                t = listB[r * KEEP + 32 + lane];
-                pk[0] = ((unsigned long long)t.x << 32) | t.y;
-                merge_keys<E, 1>(a0, a1, pk, false, lane);
+            pk[0] = EMPTY_KEY;
+            if (E == 1) {
+                sort32n<1>(a0, lane);
+            } else {
+                t = mylist[r * KEEP + 32 + lane];
+                a1[0] = ((unsigned long long)t.x << 32) | t.y;
+                merge_keys<E, 1>(a0, a1, pk, true, lane);   // sorts both halves; nothing pending
             }
             const int64_t o = (sbase + row) * KEEP + lane;
             cand_idx[o] = (int32_t)(uint32_t)a0[0];
@@ -1855,8 +1879,8 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 }
 
 static size_t ts_smem_bytes(int nslot, int E) {
-    return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * 32 * (32 * E) * 8 +
-           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)2 * BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
+    return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * 16 * (32 * E) * 8 +
+           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
            (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
 }
 // TS variant: the operand must fit the TMEM columns next to the accumulators and at least nbox+1 reference boxes must
