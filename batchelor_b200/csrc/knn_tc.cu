@@ -959,7 +959,7 @@ __device__ __forceinline__ void ts_fill_staged(const int col0, uint2* __restrict
 // One insertion is a chain of dependent warp collectives (SHFL -> VOTE -> REDUX, ~100+ cycles of latency and nothing else
 // to issue), so INS_ROWS rows are processed side by side in branch-free lock step: their chains interleave.
 #ifndef B200_INS_ROWS
-#define B200_INS_ROWS 4
+#define B200_INS_ROWS 3
 #endif
 #ifndef B200_OPT_CLZ
 #define B200_OPT_CLZ 1
@@ -1293,7 +1293,6 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         const int grp = (warp - 2) >> 2;          // 0: rows 0..15 of the quarter, 1: rows 16..31
         const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
         const int row0 = q4 * 32 + grp * 16;      // first of this warp's 16 rows (CTA-relative)
-        const int half = lane >> 4;               // which 32-column half of a load this thread holds
         uint2* mylist = lists + (size_t)(warp - 2) * 16 * KEEP;                      // this warp's candidate lists
         float4* stg = stage_all + (size_t)(warp - 2) * 8 * 32;
         volatile float* thr_pub = thr_s + row0;                                      // read by the producer's stop test
@@ -1606,11 +1605,12 @@ __global__ void prep_operand_kernel(const double* __restrict__ X, int64_t n, int
 // K3: exact fp64 re-rank + certificate.  One warp per query, one candidate per lane per round.
 // ------------------------------------------------------------------------------------------------
 constexpr int RR_WARPS = 4;
-constexpr int RR_DCH = 32;  // dims staged per chunk
-constexpr int RR_MAXROUNDS = MAX_SPLIT * 2;
+constexpr int RR_DCH = 16;  // dims staged per chunk (small staging tile + few registers: the gather is latency-bound, occupancy pays)
+constexpr int RR_MAXROUNDS = MAX_SPLIT * 2;   // most candidate lists a query can have (splits x E)
 
 __device__ __forceinline__ bool pair_less(double da, int ia, double db, int ib) { return da < db || (da == db && ia < ib); }
 
+template <int MAXR /* candidate lists of 32 per query this instance can hold */>
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_t nq, int d, int k,
               const int32_t* __restrict__ cand_idx, const float* __restrict__ thr, int nsplit, int ncand_per_split,
@@ -1629,14 +1629,14 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
     if (q < 0) return;                                          // padding slot of the grouped query order
     const int ncand = nsplit * ncand_per_split;
     const int rounds = ncand / 32;
-    double cd[RR_MAXROUNDS];
-    int ci[RR_MAXROUNDS];
+    double cd[MAXR];
+    int ci[MAXR];
 #pragma unroll
-    for (int r = 0; r < RR_MAXROUNDS; ++r) { cd[r] = INFINITY; ci[r] = -1; }
+    for (int r = 0; r < MAXR; ++r) { cd[r] = INFINITY; ci[r] = -1; }
     const double* qv = Q + q * d;
 
 #pragma unroll
-    for (int r = 0; r < RR_MAXROUNDS; ++r) {
+    for (int r = 0; r < MAXR; ++r) {
         if (r < rounds) {
             const int c = r * 32 + lane;
             const int sp = c / ncand_per_split, within = c % ncand_per_split;
@@ -1646,10 +1646,13 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
             double acc = 0.0;
             for (int t0 = 0; t0 < d; t0 += RR_DCH) {
                 const int len = min(RR_DCH, d - t0);
-                // cooperative, coalesced staging of 32 candidate rows (chunk of dims) into shared memory
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int rid = __shfl_sync(0xffffffffu, id, rr);
-                    if (lane < len) stage[warp][rr][lane] = (rid >= 0) ? X[(int64_t)rid * d + t0 + lane] : 0.0;
+                // cooperative staging of 32 candidate rows (chunk of 16 dims = one 128-byte line per row) into shared memory:
+                // each half-warp fetches one row per step, all 16 steps independent
+                const int sub = lane & 15, hw = lane >> 4;
+#pragma unroll 4
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int rid = __shfl_sync(0xffffffffu, id, 2 * rr + hw);
+                    if (sub < len) stage[warp][2 * rr + hw][sub] = (rid >= 0) ? X[(int64_t)rid * d + t0 + sub] : 0.0;
                 }
                 __syncwarp();
                 for (int t = 0; t < len; ++t) {
@@ -1692,7 +1695,7 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
         double bd = INFINITY;
         int bi = 0x7fffffff, br = -1;
 #pragma unroll
-        for (int r = 0; r < RR_MAXROUNDS; ++r)
+        for (int r = 0; r < MAXR; ++r)
             if (r < rounds && ci[r] >= 0 && pair_less(cd[r], ci[r], bd, bi)) { bd = cd[r]; bi = ci[r]; br = r; }
         double wd = bd;
         int wi = bi;
@@ -1704,7 +1707,7 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
         }
         if (wi == bi && br >= 0) {  // this lane owned the winner: retire it
 #pragma unroll
-            for (int r = 0; r < RR_MAXROUNDS; ++r)
+            for (int r = 0; r < MAXR; ++r)
                 if (r == br) ci[r] = -1;
         }
         if (lane == 0) {
@@ -2248,7 +2251,9 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         return 0;
     }
     const unsigned rr_grid = (unsigned)ceil_div(nslots, RR_WARPS);
-    rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
+    const int rr_lists = nsplit * per / 32;
+    auto rr_kernel = rr_lists == 1 ? rerank_kernel<1> : (rr_lists == 2 ? rerank_kernel<2> : rerank_kernel<RR_MAXROUNDS>);
+    rr_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
                                                          d_dist, flag_count, flag_list, nullptr, qmap1, qcount1, two_tier ? 1 : 0, qerr, bmax_bits, refmap);
     B200_LAUNCH_CHECK();
     const int* rescue_count = flag_count;
@@ -2266,7 +2271,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
             qc2 = nslots2;
         }
         B200_TRY(launch_candidates(false, qm2, qc2, prune2, false));
-        rerank_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
+        rr_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
                                                              d_dist, flag_count2, flag_list2, nullptr, qm2, qc2, 0, qerr, bmax_bits, refmap);
         B200_LAUNCH_CHECK();
         rescue_count = flag_count2;
