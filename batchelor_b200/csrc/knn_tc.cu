@@ -863,16 +863,15 @@ knn_candidates_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 //  * Tiles are 128 references wide and THREE accumulator stages (3 x 128 columns) sit next to the A columns.
 //  * Measured: with the tensor pipe busy, a lone epilogue warp per scheduler issues one ALU instruction every ~5
 //    cycles (fixed-latency stalls, nothing to switch to), which made the epilogue -- not the MMAs -- the bound.  So
-//    the epilogue runs EIGHT warps, two per scheduler: warps w and w+4 own the same TMEM lane quarter (the same 32
-//    query rows) and each scans one 64-column half of every tile.  A stage is released as soon as both halves are in
-//    registers (TMEM loads take ~30 cycles), so the MMA pipeline always has ~3 tiles of slack.
-//  * Every epilogue warp keeps its OWN candidate list per row (the KEEP best scores of the columns it scanned),
-//    unsorted, in shared memory: a hit replaces the current maximum (one vote to find its holder, one REDUX for the
-//    new maximum = the new threshold).  No pending buffers, no locks between the warps of a pair, and no capacity that
-//    could overflow: the lists of the two warps are merged once, after the stream.  With cluster pruning nearly every
-//    scored tile belongs to the queries' own component, so hits are frequent and their cost -- not the quiet path --
-//    decides the kernel time; the former sorted-list-with-pending-segment scheme spent 5 of 9 k cycles per tile in
-//    bitonic merges and lock waits there.
+//    the epilogue runs EIGHT warps, two per scheduler: warps w and w+4 read the same TMEM lane quarter and split its
+//    ROWS (16 query rows each, all 128 columns of a tile: tcgen05.ld 16x32bx2).  A stage is released as soon as the
+//    tile is in registers (TMEM loads take ~30 cycles), so the MMA pipeline always has ~3 tiles of slack.
+//  * Every row has ONE candidate list (its KEEP best scores, unsorted, in shared memory) and one owning warp: a hit
+//    replaces the current maximum (one vote to find its holder, one REDUX for the new maximum = the new threshold).
+//    No pending buffers, no locks, no capacity that could overflow, nothing shared between warps.  With cluster
+//    pruning nearly every scored tile belongs to the queries' own component, so hits are frequent and their cost --
+//    not the quiet path -- decides the kernel time; the former sorted-list-with-pending-segment scheme spent 5 of 9 k
+//    cycles per tile in bitonic merges and lock waits there.
 constexpr int TS_BN = 128;                   // references per tile
 constexpr int TS_STAGES = 3;                 // accumulator stages in TMEM
 constexpr int TS_B_BOX_BYTES = TS_BN * 128;  // 16 KB
@@ -954,8 +953,10 @@ __device__ __forceinline__ void ts_fill_staged(const int col0, uint2* __restrict
     }
     __syncwarp();
 }
-// Hits of one chunk: for every hitting row L the 32 lanes each look at ONE score of that row; every score below the
-// row's threshold replaces the current maximum of the row's list.  Invariant: thr (register of lane L) == max of list L.
+// Hits of one staged load: a holder lane L carries 32 columns of row L & 15.  For every hitting holder the 32 lanes each
+// look at ONE of its scores; every score below the row's threshold replaces the current maximum of the row's list.
+// Invariant: thr (register of both holder lanes of a row) == max of the row's list.  The caller passes the holders of
+// the left and of the right 32 columns in separate calls, so no two slots of a group work on the same row.
 // One insertion is a chain of dependent warp collectives (SHFL -> VOTE -> REDUX, ~100+ cycles of latency and nothing else
 // to issue), so INS_ROWS rows are processed side by side in branch-free lock step: their chains interleave.
 #ifndef B200_INS_ROWS

@@ -294,7 +294,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "fp16x3 tensor-core scoring (fp32 accumulate) + fp64 exact re-rank", "data": "synthetic",
+            "dtype": "fp16 tensor-core scoring (one-term tier, fp16x3 re-score of uncertified queries; fp32 accumulate) + fp64 exact re-rank", "data": "synthetic",
             "config": workload_config(args, {"parallelism": f"query rows sharded over {world} GPU(s), reference batch replicated, "
                                                             f"NCCL all-gather of per-shard top-k" if world > 1 else "single GPU",
                                              "mnn_pairs": npairs}),
