@@ -32,6 +32,7 @@ class B200Error(RuntimeError):
 SIGNATURES = {
     "b200mnn_last_error": [],
     "b200mnn_version": [],
+    "b200mnn_launch_count": [],
     "b200mnn_device_count": [],
     "b200mnn_set_device": [C.c_int],
     "b200mnn_query_knn": [f64p, i64, f64p, i64, C.c_int, C.c_int, C.c_int, i32p, f64p],
@@ -74,7 +75,7 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here means header and library disagree
             fn.argtypes = argtypes
-            fn.restype = C.c_char_p if name == "b200mnn_last_error" else C.c_int
+            fn.restype = C.c_char_p if name == "b200mnn_last_error" else (C.c_int64 if name == "b200mnn_launch_count" else C.c_int)
         _lib = lib
     return _lib
 

@@ -1,6 +1,7 @@
 // Error plumbing, device selection and stream-ordered scratch memory for libb200mnn.
 #include "common.cuh"
 
+#include <atomic>
 #include <mutex>
 
 namespace b200 {
@@ -8,6 +9,9 @@ namespace b200 {
 static thread_local std::string g_last_error;
 
 void set_error(const std::string& msg) { g_last_error = msg; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -81,6 +85,7 @@ extern "C" {
 
 const char* b200mnn_last_error(void) { return b200::g_last_error.c_str(); }
 int b200mnn_version(void) { return 100; }
+int64_t b200mnn_launch_count(void) { return (int64_t)b200::g_launches.load(); }
 
 int b200mnn_device_count(void) {
     int n = 0;

@@ -28,8 +28,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
         if (_rc != 0) return _rc; \
     } while (0)
 
-// Checks the launch that just happened (configuration errors surface here, execution errors at the next sync).
-#define B200_LAUNCH_CHECK() B200_CUDA(cudaGetLastError())
+// Checks the launch that just happened (configuration errors surface here, execution errors at the next sync) and
+// counts it (b200mnn_launch_count: what bench.py reports as gpu_launches).
+void count_launch();
+#define B200_LAUNCH_CHECK()             \
+    do {                                \
+        ::b200::count_launch();         \
+        B200_CUDA(cudaGetLastError());  \
+    } while (0)
 
 int ensure_device();  // B200MNN_ECUDA if no usable device
 

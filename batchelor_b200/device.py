@@ -17,7 +17,8 @@ _launches = 0  # kernels of libb200mnn launched through this module (bench.py re
 
 
 def launches() -> int:
-    return _launches
+    """Kernels of libb200mnn launched by this process so far (counted inside the library at every launch site)."""
+    return int(_lib.load().b200mnn_launch_count())
 
 
 def _count(n: int) -> None:

@@ -52,6 +52,8 @@ extern "C" {
 
 const char* b200mnn_last_error(void);
 int b200mnn_version(void);
+/* Kernels of this library launched so far by the calling process (every launch site counts itself). */
+int64_t b200mnn_launch_count(void);
 /* Number of visible CUDA devices (0 if none / no driver). */
 int b200mnn_device_count(void);
 /* Select the device used by this thread's subsequent calls (cudaSetDevice). */
