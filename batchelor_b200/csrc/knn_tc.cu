@@ -1621,7 +1621,8 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
               const int32_t* __restrict__ qmap, const int* __restrict__ qcount,   // optional: list slot j holds query qmap[j], j < *qcount
               const int fast /* candidates came from the one-term schedule: wider error bound */,
               const float2* __restrict__ qerr, const unsigned int* __restrict__ bmax_bits,
-              const int32_t* __restrict__ refmap /* optional: candidate ids are rows of the grouped operand -> original rows */) {
+              const int32_t* __restrict__ refmap /* optional: candidate ids are rows of the grouped operand -> original rows */,
+              double* __restrict__ flag_dk2 /* optional, parallel to flag_list: exact squared distance of the k-th candidate */) {
     __shared__ double stage[RR_WARPS][32][RR_DCH + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t jq = (int64_t)blockIdx.x * RR_WARPS + warp;   // slot in the candidate / threshold arrays
@@ -1742,6 +1743,7 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
         if (!(ok)) {
             const int slot = atomicAdd(flag_count, 1);
             flag_list[slot] = (int32_t)q;
+            if (flag_dk2) flag_dk2[slot] = dk;   // +inf when the query has fewer than k candidates
         }
     }
 }
@@ -1751,28 +1753,35 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
 // pairs strictly greater than the previous pick.  O(k n d) per query -- only for rare queries.
 // ------------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
+constexpr int RS_CAP = 1024;   // references a block can collect in its single-pass mode
 
+// flag_dk2 (optional, parallel to flag_list): the exact squared distance of the query's k-th candidate -- an upper bound
+// of its true k-th neighbour distance.  With it a block needs ONE pass over the references: it collects every reference
+// within that bound (normally a few dozen: the neighbours plus the ties that defeated the certificate) and selects among
+// those; only if more than RS_CAP qualify does it fall back to k full passes.
 __global__ void __launch_bounds__(RS_THREADS)
 rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Q, int d, int k,
-              const int* __restrict__ flag_count, const int32_t* __restrict__ flag_list, int64_t nq_all,
+              const int* __restrict__ flag_count, const int32_t* __restrict__ flag_list, const double* __restrict__ flag_dk2, int64_t nq_all,
               int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
     __shared__ double sd[RS_THREADS / 32];
     __shared__ int si[RS_THREADS / 32];
     __shared__ double pick_d;
     __shared__ int pick_i;
+    __shared__ double col_d[RS_CAP];
+    __shared__ int col_i[RS_CAP];
+    __shared__ int col_n;
     extern __shared__ double qs[];  // [d]
     const int count = flag_list ? *flag_count : (int)nq_all;
     for (int f = blockIdx.x; f < count; f += gridDim.x) {
         const int64_t q = flag_list ? flag_list[f] : f;
         __syncthreads();
         for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = Q[q * d + t];
-        if (threadIdx.x == 0) { pick_d = -1.0; pick_i = -1; }
+        if (threadIdx.x == 0) { pick_d = -1.0; pick_i = -1; col_n = 0; }
         __syncthreads();
-        for (int j = 0; j < k; ++j) {
-            const double pd = pick_d;
-            const int pi = pick_i;
-            double bd = INFINITY;
-            int bi = 0x7fffffff;
+        // single-pass collection of everything within the bound
+        bool collected = false;
+        const double bound = (flag_list && flag_dk2) ? flag_dk2[f] : INFINITY;
+        if (bound < INFINITY) {
             for (int64_t r = threadIdx.x; r < n; r += blockDim.x) {
                 const double* xv = X + r * d;
                 double acc = 0.0;
@@ -1780,7 +1789,35 @@ rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict_
                     const double df = __dsub_rn(qs[t], xv[t]);
                     acc = __dadd_rn(acc, __dmul_rn(df, df));
                 }
-                const int ri = (int)r;
+                if (acc <= bound) {
+                    const int pos = atomicAdd(&col_n, 1);
+                    if (pos < RS_CAP) { col_d[pos] = acc; col_i[pos] = (int)r; }
+                }
+            }
+            __syncthreads();
+            collected = col_n <= RS_CAP;   // (col_n >= k always: the k candidates themselves qualify)
+        }
+        const int64_t nscan = collected ? (int64_t)col_n : n;
+        for (int j = 0; j < k; ++j) {
+            const double pd = pick_d;
+            const int pi = pick_i;
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            for (int64_t r = threadIdx.x; r < nscan; r += blockDim.x) {
+                double acc;
+                int ri;
+                if (collected) {
+                    acc = col_d[r];
+                    ri = col_i[r];
+                } else {
+                    const double* xv = X + r * d;
+                    acc = 0.0;
+                    for (int t = 0; t < d; ++t) {
+                        const double df = __dsub_rn(qs[t], xv[t]);
+                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    }
+                    ri = (int)r;
+                }
                 const bool after = acc > pd || (acc == pd && ri > pi);  // strictly after the previous pick
                 if (after && pair_less(acc, ri, bd, bi)) { bd = acc; bi = ri; }
             }
@@ -1973,7 +2010,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         if (dbg) return fail(B200MNN_EINVAL, "debug candidates requested for a shape outside the tensor path");
         // generic exact path: every query through the rescue kernel
         const int grid = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 8);
-        rescue_kernel<<<grid, RS_THREADS, (size_t)std::max(d, 1) * sizeof(double), stream>>>(dX, n, dQ, d, k, nullptr, nullptr, nq, d_idx, d_dist);
+        rescue_kernel<<<grid, RS_THREADS, (size_t)std::max(d, 1) * sizeof(double), stream>>>(dX, n, dQ, d, k, nullptr, nullptr, nullptr, nq, d_idx, d_dist);
         B200_LAUNCH_CHECK();
         if (d_stats) { write_stats_kernel<<<1, 1, 0, stream>>>(nullptr, d_stats, 0, 0); B200_LAUNCH_CHECK(); }
         return 0;
@@ -2020,6 +2057,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     float* thr = ws.get<float>((size_t)nsplit * nslots);
     int32_t* flag_list = ws.get<int32_t>((size_t)nq);
     int32_t* flag_list2 = ws.get<int32_t>((size_t)nq);
+    double* flag_dk2 = ws.get<double>((size_t)nq);   // bound for the exact rescue (of whichever re-rank flags last)
     float2* qerr = ws.get<float2>((size_t)nq_pad);
     unsigned char* scalars = ws.get<unsigned char>(64);
     unsigned long long* visited = ws.get<unsigned long long>(2);
@@ -2255,7 +2293,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     const int rr_lists = nsplit * per / 32;
     auto rr_kernel = rr_lists == 1 ? rerank_kernel<1> : (rr_lists == 2 ? rerank_kernel<2> : rerank_kernel<RR_MAXROUNDS>);
     rr_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
-                                                         d_dist, flag_count, flag_list, nullptr, qmap1, qcount1, two_tier ? 1 : 0, qerr, bmax_bits, refmap);
+                                                         d_dist, flag_count, flag_list, nullptr, qmap1, qcount1, two_tier ? 1 : 0, qerr, bmax_bits, refmap, flag_dk2);
     B200_LAUNCH_CHECK();
     const int* rescue_count = flag_count;
     const int32_t* rescue_list = flag_list;
@@ -2273,12 +2311,12 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         }
         B200_TRY(launch_candidates(false, qm2, qc2, prune2, false));
         rr_kernel<<<rr_grid, RR_WARPS * 32, 0, stream>>>(dX, dQ, nslots, d, k, cand_idx, thr, nsplit, per, scale_exp, qnorm, maxnorm_bits, d_idx,
-                                                             d_dist, flag_count2, flag_list2, nullptr, qm2, qc2, 0, qerr, bmax_bits, refmap);
+                                                             d_dist, flag_count2, flag_list2, nullptr, qm2, qc2, 0, qerr, bmax_bits, refmap, flag_dk2);
         B200_LAUNCH_CHECK();
         rescue_count = flag_count2;
         rescue_list = flag_list2;
     }
-    rescue_kernel<<<sm_count() * 4, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, k, rescue_count, rescue_list, nq, d_idx, d_dist);
+    rescue_kernel<<<sm_count() * 4, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, k, rescue_count, rescue_list, flag_dk2, nq, d_idx, d_dist);
     B200_LAUNCH_CHECK();
     if (d_stats) {
         write_stats_kernel<<<1, 1, 0, stream>>>(rescue_count, d_stats, nsplit, use_prune ? 2 : 1, two_tier ? flag_count : nullptr, use_ts ? visited : nullptr,

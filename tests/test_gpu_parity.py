@@ -158,6 +158,41 @@ def test_query_knn_pruned_skips_tiles_and_stays_exact(monkeypatch):
     assert np.array_equal(dist.cpu().numpy(), want_dist)
 
 
+@pytest.mark.parametrize("n,nq,d,k,ncomp,nclus", [
+    (40_000, 25_000, 32, 30, 12, 32),     # 64-entry lists, two operand boxes in the first tier
+    (50_000, 20_000, 64, 50, 6, 16),
+    (30_000, 30_000, 20, 5, 40, 64),      # many small components
+    (20_000, 70_000, 50, 20, 3, 128),     # far more clusters than components
+])
+def test_query_knn_pruned_medium_against_kmknn_port(n, nq, d, k, ncomp, nclus, monkeypatch):
+    monkeypatch.setenv("B200MNN_PRUNE", "1")
+    monkeypatch.setenv("B200MNN_CLUSTERS", str(nclus))
+    X, Q = synth.pc_batches(2, [n, nq], d=d, ncomp=ncomp)
+    got = bb.queryKNN(X, Q, k)
+    idx, dist = capi.Kmknn(X).query(Q, k)
+    assert int((got["index"] != idx).sum()) == 0
+    assert np.array_equal(got["distance"], dist)
+
+
+def test_query_knn_many_exact_duplicates_go_through_the_bounded_rescue():
+    """40 copies of every location: every query has > 32 equidistant candidates at its k-th distance, so no scoring tier
+    can certify it; the exact rescue (one bounded pass per query) must still return the (distance, index) order."""
+    import torch
+    from batchelor_b200 import device as dev
+
+    base, _ = synth.pc_batches(2, [2_000, 10], d=50, ncomp=8)
+    X = np.repeat(base, 40, axis=0)                      # 80,000 references: pruned path
+    Q = base[::2] + 0.0                                  # 1,000 queries sitting on duplicated locations
+    Q = np.concatenate([Q] * 17)                         # >= 16,384 queries
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    idx, dist = dev.query_knn(torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda(), 20, stats=stats)
+    s = stats.cpu().numpy()
+    assert s[0] > 0, "expected uncertifiable queries"
+    want_idx, want_dist = capi.Kmknn(X).query(Q, 20)
+    assert int((idx.cpu().numpy() + 1 != want_idx).sum()) == 0
+    assert np.array_equal(dist.cpu().numpy(), want_dist)
+
+
 def test_query_knn_dense_path_still_exact_at_medium_size(monkeypatch):
     monkeypatch.setenv("B200MNN_PRUNE", "0")
     X, Q = synth.pc_batches(2, [70_000, 20_000], d=50)
