@@ -243,19 +243,32 @@ __global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restric
     if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + c, __popc(peers));
 }
 
-// tile0[c]: first reference tile of cluster c; slot0[c]: first query slot; cursors zeroed.
+// tile0[c]: first reference tile of cluster c; slot_base[c]: first query slot of cluster c; cursors zeroed.  Query
+// slots are laid out by DESCENDING reference count of their cluster: a query tile's work is roughly the size of its own
+// cluster, and starting the heavy CTAs first shortens the tail of the scoring kernel.
 __global__ void offsets_kernel(const int* __restrict__ cnt_ref, const int* __restrict__ cnt_q, int C, int* __restrict__ tile0,
                                int* __restrict__ row_base, int* __restrict__ slot_base, int* __restrict__ nslots, int* __restrict__ cursors) {
+    __shared__ int order[CL_MAXC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // rank of cluster c by (reference count descending, id ascending)
+        int rank = 0;
+        for (int o = 0; o < C; ++o) rank += (cnt_ref[o] > cnt_ref[c] || (cnt_ref[o] == cnt_ref[c] && o < c)) ? 1 : 0;
+        order[rank] = c;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        int t = 0, s = 0;
+        int t = 0;
         for (int c = 0; c < C; ++c) {
             tile0[c] = t;
             row_base[c] = t * CL_TILE;
-            slot_base[c] = s;
             t += (cnt_ref[c] + CL_TILE - 1) / CL_TILE;
-            s += ((cnt_q[c] + CL_TILE - 1) / CL_TILE) * CL_TILE;
         }
         tile0[C] = t;
+        int s = 0;
+        for (int i = 0; i < C; ++i) {
+            const int c = order[i];
+            slot_base[c] = s;
+            s += ((cnt_q[c] + CL_TILE - 1) / CL_TILE) * CL_TILE;
+        }
         *nslots = s;
     }
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) cursors[c] = 0;

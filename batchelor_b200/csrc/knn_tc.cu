@@ -1394,35 +1394,24 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             dbg_ts[(warp - 2) * 8 + 7] = seq;
             for (int i = 0; i < 7; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = stat[3 + i];
         }
-        // Output: every warp sorts and writes its 16 rows.  The KEEP-th best score is the row's threshold: a rejected or
-        // evicted score was >= the list maximum at that time, which only ever decreases.
+        // Output: every warp writes its 16 lists as they are (the re-rank orders the candidates by their exact distances
+        // anyway).  The list maximum -- this lane's thr, +inf while fewer than KEEP references were seen -- is the row's
+        // threshold: a rejected or evicted score was >= the maximum at that time, which only ever decreases.
         const int64_t rowbase = (int64_t)m0 + row0;
         const int64_t sbase = (int64_t)blockIdx.y * nq;
 #pragma unroll 1
         for (int r = 0; r < 16; ++r) {
             const int64_t row = rowbase + r;
             if (row >= nq_eff) break;   // warp-uniform
-            unsigned long long a0[1], a1[1], pk[1];
-            uint2 t = mylist[r * KEEP + lane];
-            a0[0] = ((unsigned long long)t.x << 32) | t.y;
-            a1[0] = EMPTY_KEY;
-            pk[0] = EMPTY_KEY;
-            if (E == 1) {
-                sort32n<1>(a0, lane);
-            } else {
-                t = mylist[r * KEEP + 32 + lane];
-                a1[0] = ((unsigned long long)t.x << 32) | t.y;
-                merge_keys<E, 1>(a0, a1, pk, true, lane);   // sorts both halves; nothing pending
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const uint2 t = mylist[r * KEEP + 32 * e + lane];
+                const int64_t o = (sbase + row) * KEEP + 32 * e + lane;
+                cand_idx[o] = (int32_t)t.y;                       // empty entries carry id -1
+                if (cand_score) cand_score[o] = ord_float(t.x);
             }
-            const int64_t o = (sbase + row) * KEEP + lane;
-            cand_idx[o] = (int32_t)(uint32_t)a0[0];
-            if (cand_score) cand_score[o] = key_score(a0[0]);
-            if (E == 2) {
-                cand_idx[o + 32] = (int32_t)(uint32_t)a1[0];
-                if (cand_score) cand_score[o + 32] = key_score(a1[0]);
-            }
-            if (lane == 31) thr_out[sbase + row] = key_score(E == 1 ? a0[0] : a1[0]);   // +inf while fewer than KEEP references were seen
         }
+        if (lane < 16 && rowbase + lane < nq_eff) thr_out[sbase + rowbase + lane] = thr;
         tc_fence_before();
     }
     __syncthreads();
