@@ -906,7 +906,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const u
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // Order-preserving map float -> uint32 (the high word of make_key) and back.
 __device__ __forceinline__ uint32_t ord_bits(float s) {
@@ -922,6 +921,13 @@ __device__ __forceinline__ uint32_t sel_u32(const bool c, const uint32_t a, cons
     uint32_t r;
     asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.b32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)c));
     return r;
+}
+
+// Conditional replacement of a list entry (score bits, id) under ONE predicate, as straight-line code.
+__device__ __forceinline__ void sel_entry(const bool c, const uint32_t score, const uint32_t id, uint2& e) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\tselp.b32 %0, %2, %0, p;\n\tselp.b32 %1, %3, %1, p;\n\t}"
+        : "+r"(e.x), "+r"(e.y)
+        : "r"(score), "r"(id), "r"((uint32_t)c));
 }
 
 // Stages one 32x32 chunk of scores (registers, lane = row) in shared memory, XOR-swizzled so that both these row-wise
@@ -962,15 +968,6 @@ __device__ __forceinline__ void ts_fill_staged(const int col0, uint2* __restrict
 #ifndef B200_INS_ROWS
 #define B200_INS_ROWS 3
 #endif
-#ifndef B200_OPT_CLZ
-#define B200_OPT_CLZ 1
-#endif
-#ifndef B200_OPT_HOLDER
-#define B200_OPT_HOLDER 1
-#endif
-#ifndef B200_OPT_MASK
-#define B200_OPT_MASK 0
-#endif
 template <int E>
 __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, float& thr, uint2* __restrict__ list,
                                                  volatile float* __restrict__ thr_pub, const float4* __restrict__ stg, const int lane, long long* stat) {
@@ -989,13 +986,8 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
         float thrL[NR], sc[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
-#if B200_OPT_CLZ
             L[i] = 31 - __clz(hit);                      // highest hitting row first (FLO; ffs would need BREV + FLO); -1: slot unused,
             hit &= ~((L[i] >= 0 ? 1u : 0u) << (L[i] & 31));   // rides along on row L[0], never stored
-#else
-            L[i] = hit ? __ffs(hit) - 1 : -1;            // -1: slot unused (rides along on row L[0], never stored)
-            hit &= hit - 1;
-#endif
         }
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
@@ -1025,13 +1017,8 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 act[i] = m[i] != 0u;
-#if B200_OPT_CLZ
                 const int j = act[i] ? 31 - __clz(m[i]) : 0;   // any order of the row's hits will do
                 m[i] &= ~((act[i] ? 1u : 0u) << j);
-#else
-                const int j = act[i] ? __ffs(m[i]) - 1 : 0;
-                m[i] &= m[i] - 1u;
-#endif
                 any |= m[i];
                 idj[i] = (uint32_t)(col0 + ((L[i] >> 4) & 1) * 32 + j);
                 sj[i] = __shfl_sync(0xffffffffu, so[i], j);
@@ -1044,29 +1031,13 @@ __device__ __forceinline__ void ts_insert_staged(unsigned hit, const int col0, f
 #pragma unroll
             for (int i = 0; i < NR; ++i) {
                 const bool doit = act[i] && sj[i] < curmax[i];
-                // any holder of the maximum will do: the highest such lane.  Bit-mask selects: the compiler cannot turn them
-                // back into branches (the rounds must stay straight-line code so that the rows' chains interleave).
-#if B200_OPT_HOLDER
+                // any holder of the maximum will do: the highest such lane.  sel_entry is inline PTX (setp + 2 selp): the
+                // compiler cannot turn it back into a branch, so the rounds stay straight-line code and the rows' chains interleave.
                 const bool in0 = doit && (E == 1 || b0[i] != 0u) && lane == 31 - __clz(b0[i]);
-#else
-                const bool in0 = doit && (E == 1 || b0[i] != 0u) && lane == __ffs(b0[i]) - 1;
-#endif
-#if B200_OPT_MASK
-                const uint32_t k0 = in0 ? 0xffffffffu : 0u;
-                e0[i].x = (sj[i] & k0) | (e0[i].x & ~k0);
-                e0[i].y = (idj[i] & k0) | (e0[i].y & ~k0);
-#else
-                e0[i].x = sel_u32(in0, sj[i], e0[i].x);
-                e0[i].y = sel_u32(in0, idj[i], e0[i].y);
-#endif
+                sel_entry(in0, sj[i], idj[i], e0[i]);
                 if (E == 2) {
-#if B200_OPT_HOLDER
                     const bool in1 = doit && b0[i] == 0u && lane == 31 - __clz(b1[i]);
-#else
-                    const bool in1 = doit && b0[i] == 0u && lane == __ffs(b1[i]) - 1;
-#endif
-                    e1[i].x = sel_u32(in1, sj[i], e1[i].x);
-                    e1[i].y = sel_u32(in1, idj[i], e1[i].y);
+                    sel_entry(in1, sj[i], idj[i], e1[i]);
                 }
             }
 #pragma unroll
