@@ -146,12 +146,53 @@ def find_mutual_nns(left: torch.Tensor, right: torch.Tensor) -> Tuple[torch.Tens
     return first[:m], second[:m]
 
 
+_side_streams = {}
+
+
+def _two_side_streams(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _side_streams[key]
+
+
 def find_mutual_nn(data1: torch.Tensor, data2: torch.Tensor, k1: int, k2: int, sharded: bool = True):
-    """findMutualNN(data1, data2, k1, k2): two exact searches + mutual pairs.  Returns (first, second, w21, w12)."""
-    knn = query_knn_sharded if sharded else query_knn
+    """findMutualNN(data1, data2, k1, k2): two exact searches + mutual pairs.  Returns (first, second, w21, w12).
+
+    The two searches are independent, so their kernels are enqueued on two side streams: the serial stretches of one
+    direction's cluster plan (a one-block seeding kernel, small scans) overlap with the other direction's work.  With a
+    process group the local shards are computed that way and the two all-gathers follow on the caller's stream."""
+    import torch.distributed as dist_
+
     k1 = min(k1, data1.shape[0]); k2 = min(k2, data2.shape[0])
-    w21, _ = knn(data2, data1, k2, want_dist=False)  # neighbours of batch-1 cells in batch 2
-    w12, _ = knn(data1, data2, k1, want_dist=False)  # neighbours of batch-2 cells in batch 1
+    n1, n2 = data1.shape[0], data2.shape[0]
+    ws = dist_.get_world_size() if (sharded and dist_.is_available() and dist_.is_initialized()) else 1
+    split1 = ws > 1 and n1 >= ws * 2048     # batch-1 cells are the queries of the first search
+    split2 = ws > 1 and n2 >= ws * 2048
+    rank = dist_.get_rank() if ws > 1 else 0
+    lo1, hi1, per1 = shard_bounds(n1, ws, rank) if split1 else (0, n1, n1)
+    lo2, hi2, per2 = shard_bounds(n2, ws, rank) if split2 else (0, n2, n2)
+    cur = torch.cuda.current_stream()
+    s1, s2 = _two_side_streams(data1.device)
+    s1.wait_stream(cur); s2.wait_stream(cur)
+    with torch.cuda.stream(s1):
+        a, _ = query_knn(data2, data1[lo1:hi1], k2, want_dist=False)   # neighbours of batch-1 cells in batch 2
+    with torch.cuda.stream(s2):
+        b, _ = query_knn(data1, data2[lo2:hi2], k1, want_dist=False)   # neighbours of batch-2 cells in batch 1
+    cur.wait_stream(s1); cur.wait_stream(s2)
+    a.record_stream(cur); b.record_stream(cur)
+
+    def gather(local, n, k, per, lo, hi, split):
+        if not split:
+            return local
+        pad = torch.zeros((per, k), dtype=torch.int32, device=local.device)
+        pad[: hi - lo] = local
+        full = torch.empty((ws * per, k), dtype=torch.int32, device=local.device)
+        dist_.all_gather_into_tensor(full, pad)
+        return full[:n]
+
+    w21 = gather(a, n1, k2, per1, lo1, hi1, split1)
+    w12 = gather(b, n2, k1, per2, lo2, hi2, split2)
     first, second = find_mutual_nns(w21, w12)
     return first, second, w21, w12
 
