@@ -4,7 +4,9 @@
 #include "internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
+#include <string>
 #include <vector>
 
 namespace b200 {
@@ -22,6 +24,31 @@ static cudaStream_t lib_stream() {
         if (cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     }
     return streams[dev];
+}
+
+// Two side streams and three events per device (created lazily): the two searches of findMutualNN are independent, so
+// their kernels are enqueued side by side -- the serial stretches of one direction's cluster plan overlap with the other.
+struct SideStreams {
+    cudaStream_t a = nullptr, b = nullptr;
+    cudaEvent_t start = nullptr, done_a = nullptr, done_b = nullptr;
+};
+static SideStreams* side_streams() {
+    static std::mutex mu;
+    static std::vector<SideStreams> all;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if ((int)all.size() <= dev) all.resize(dev + 1);
+    SideStreams& ss = all[dev];
+    if (!ss.a) {
+        bool ok = cudaStreamCreateWithFlags(&ss.a, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&ss.b, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ss.start, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ss.done_a, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ss.done_b, cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); ss = SideStreams(); return nullptr; }
+    }
+    return &all[dev];
 }
 
 template <typename T>
@@ -148,8 +175,27 @@ int b200mnn_find_mutual_nn(const double* data1, int64_t n1, const double* data2,
     int32_t* dsecond = ws.get<int32_t>((size_t)std::max<int64_t>(cap, 1));
     int64_t* dnp = ws.get<int64_t>(1);
     if (!ws.ok()) return B200MNN_ENOMEM;
-    B200_TRY(knn::query_knn_device(d2, n2, d1, n1, d, k2, w21, nullptr, nullptr, s, nullptr));
-    B200_TRY(knn::query_knn_device(d1, n1, d2, n2, d, k1, w12, nullptr, nullptr, s, nullptr));
+    SideStreams* ss = getenv("B200MNN_SERIAL") ? nullptr : side_streams();   // B200MNN_SERIAL: both searches on the one stream
+    if (ss) {
+        B200_CUDA(cudaEventRecord(ss->start, s));
+        B200_CUDA(cudaStreamWaitEvent(ss->a, ss->start, 0));
+        B200_CUDA(cudaStreamWaitEvent(ss->b, ss->start, 0));
+        const int rc1 = knn::query_knn_device(d2, n2, d1, n1, d, k2, w21, nullptr, nullptr, ss->a, nullptr);
+        const int rc2 = rc1 ? 0 : knn::query_knn_device(d1, n1, d2, n2, d, k1, w12, nullptr, nullptr, ss->b, nullptr);
+        if (rc1 || rc2) {   // the scratch buffers must outlive whatever was enqueued on the side streams
+            const std::string msg = b200mnn_last_error();
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+            return fail(rc1 ? rc1 : rc2, msg);
+        }
+        B200_CUDA(cudaEventRecord(ss->done_a, ss->a));
+        B200_CUDA(cudaEventRecord(ss->done_b, ss->b));
+        B200_CUDA(cudaStreamWaitEvent(s, ss->done_a, 0));
+        B200_CUDA(cudaStreamWaitEvent(s, ss->done_b, 0));
+    } else {
+        B200_TRY(knn::query_knn_device(d2, n2, d1, n1, d, k2, w21, nullptr, nullptr, s, nullptr));
+        B200_TRY(knn::query_knn_device(d1, n1, d2, n2, d, k1, w12, nullptr, nullptr, s, nullptr));
+    }
     B200_TRY(mutual::find_mutual_nns_device(w21, n1, k2, w12, n2, k1, dfirst, dsecond, cap, dnp, 1, nullptr, s));
     int64_t np = 0;
     B200_CUDA(cudaMemcpyAsync(&np, dnp, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
