@@ -17,8 +17,9 @@ for rep in range(reps):
     torch.cuda.synchronize(); t0 = time.time()
     stats = torch.zeros(8, dtype=torch.int64, device='cuda')
     idx, dist = dev.query_knn(Xd, Qd, k, stats=stats)
+    t_enq = time.time() - t0
     torch.cuda.synchronize(); dt = time.time() - t0
     kms, kl, kf = C.c_double(0), C.c_int64(0), C.c_double(0)
     _lib.call("b200mnn_profile_collect", C.byref(kms), C.byref(kl), C.byref(kf))
     _lib.call("b200mnn_profile_enable", 0)
-    print(f"{n} refs x {nq} queries k={k}: {dt:.4f} s (candidates kernels {kms.value / 1e3:.4f} s, {kl.value} launches; rescued {int(stats[0])}, tier-2 queries {int(stats[3])}, path {int(stats[2])}, tiles scored {int(stats[4])}+{int(stats[5])} of {int(stats[6])} dense)")
+    print(f"{n} refs x {nq} queries k={k}: {dt:.4f} s (host enqueue {t_enq * 1e3:.2f} ms; candidates kernels {kms.value / 1e3:.4f} s, {kl.value} launches; rescued {int(stats[0])}, tier-2 queries {int(stats[3])}, path {int(stats[2])}, tiles scored {int(stats[4])}+{int(stats[5])} of {int(stats[6])} dense)")
