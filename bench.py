@@ -182,6 +182,20 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------------------
 # this repo's CUDA path
 # ------------------------------------------------------------------------------------------------------------------
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu summary (None if absent)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_cand_ts_final_summary.csv")
+    try:
+        tot = 0.0
+        for line in open(path):
+            f = line.strip().split(",")
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[2]]
+        return tot or None
+    except OSError:
+        return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -306,7 +320,9 @@ def run_b200(args):
                            "pinned host -> device copies + device.find_mutual_nn (sharded) + pair lists back to host"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": ncu_traffic_bytes(),
+                         "traffic_note": "DRAM bytes (read + write) of one first-tier launch at 1M x 1M from the committed ncu --set full "
+                                         "capture (profiles/r1_ncu_cand_ts_final_summary.csv); the 28.9 GB of operand tiles it reads come from L2",
                          "kernel": "knn_candidates_kernel (tcgen05 fp16x3 scoring + top-k filter)",
                          "kernel_ms_per_launch": kernel_ms_max / max(kernel_launches / world, 1),
                          "kernel_share_of_step": kernel_ms_max / total_ms,
