@@ -5,22 +5,24 @@
 // (squared Euclidean distance accumulated in double in dimension order, row index) pairs, ascending.
 //
 // Pipeline (all on one stream, no host synchronisation):
-//   K0 absmax         : one power-of-two scale S so that every |x*S| < 2^15 (fp16 range, lo parts stay normal)
-//   K1 prep_operand   : fp64 row -> fp16 "hi" and "lo" K-slices (x*S = hi + lo + O(2^-22)), fp32 scaled norm,
-//                       fp64 norm.  Operand rows are K-major, 64 fp16 (128 B) per TMA box, SWIZZLE_128B.
-//   K2 knn_candidates : tcgen05 kernel.  score(q,j) = ||x_j||^2 - 2 q.x_j with q.x_j ~ qh.xh + ql.xh + qh.xl
-//                       (three fp16 MMAs per 16 dims, fp32 accumulation in TMEM; the remainder dims are packed
-//                       as one virtual slice).  One CTA = 128 queries (TMEM lanes) x a stream of 256-reference
-//                       tiles; TMA producer warp, single-thread MMA issuer, 4 epilogue warps that read the
-//                       accumulators straight out of TMEM (tcgen05.ld), compare against a per-query running
-//                       threshold held in a register and keep the 32*E best approximate scores per query in a
-//                       warp-cooperative sorted list in shared memory.
+//   K0 rowstat/scale  : fp64 norms; one power-of-two scale S so that every |x*S| < 2^15 (fp16 range, lo parts normal)
+//   P  cluster plan   : (large searches, knn_cluster.cu) k-means grouping of references and queries, per query tile the
+//                       reference clusters in ascending order of a rigorous lower bound on their distance
+//   K1 prep_operand   : fp64 row -> fp16 "hi" and "lo" K-slices (x*S = hi + lo + O(2^-22)) + the folded norm columns;
+//                       operand rows are K-major, 64 fp16 (128 B) per TMA box, SWIZZLE_128B, references in grouped order
+//   K2 knn_candidates : tcgen05 kernels (knn_candidates_ts_kernel: query operand in TMEM, the default; knn_candidates_kernel:
+//                       both operands in shared memory).  score(q,j) = S^2 (||x_j||^2 - 2 q.x_j) accumulated in fp32 in
+//                       TMEM, first with one fp16 term per 16 dims, for the queries that tier cannot certify with three
+//                       (qh.xh + ql.xh + qh.xl).  One CTA = 128 queries (TMEM lanes) x the stream of 128-reference
+//                       tiles its producer warp selects; the epilogue warps read the accumulators straight out of TMEM
+//                       (tcgen05.ld), compare against per-row running thresholds and keep the 32*E best approximate
+//                       scores of every row in a replace-the-maximum list in shared memory.
 //   K3 rerank         : exact fp64 distances of the <= nsplit*32*E candidates (same summation order as the
 //                       reference arithmetic), (distance, index) selection of the k best, and a CERTIFICATE:
 //                       the result is provably exact if d2_k < (smallest retained threshold) - eps, where eps
-//                       bounds the fp16x3/fp32 scoring error.  Uncertified queries are flagged.
-//   K4 rescue         : flagged queries are recomputed by an exact fp64 scan of all references.  This is also
-//                       the generic path for shapes the tensor path does not cover (k > 56, d > 192).
+//                       bounds the scoring error of the schedule.  Uncertified queries are flagged.
+//   K4 rescue         : queries no tier certifies are recomputed by an exact fp64 scan of the references.  This is also
+//                       the generic path for shapes the tensor path does not cover (k > 56, d > ~190).
 #include "common.cuh"
 #include "knn_cluster.cuh"
 
