@@ -90,27 +90,31 @@ def shard_bounds(nq: int, world: int, rank: int) -> Tuple[int, int, int]:
     return min(nq, rank * per), min(nq, (rank + 1) * per), per
 
 
+def all_gather_rows(local: torch.Tensor, n: int, per: int) -> torch.Tensor:
+    """Exchange step of the query-sharded search (backend-agnostic: NCCL on GPUs, gloo in the CPU tests): pads this
+    rank's block of rows to `per` rows, all-gathers the blocks of every rank in rank order and returns the first n rows."""
+    import torch.distributed as dist_
+
+    ws = dist_.get_world_size()
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    full = torch.empty((ws * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist_.all_gather_into_tensor(full, pad)
+    return full[:n]
+
+
 def shard_rows_and_gather(nq: int, k: int, compute_local, device, want_dist: bool = True):
-    """Host-side sharding logic (backend-agnostic: NCCL on GPUs, gloo in the CPU tests): every rank computes
-    `compute_local(lo, hi) -> (idx[hi-lo, k], dist or None)` for its block of rows; blocks are padded to equal size and
-    all-gathered so every rank ends with the full [nq, k] result in row order."""
+    """Host-side sharding logic: every rank computes `compute_local(lo, hi) -> (idx[hi-lo, k], dist or None)` for its
+    contiguous block of rows (:func:`shard_bounds`); the blocks are exchanged with :func:`all_gather_rows`, so every rank
+    ends with the full [nq, k] result in row order."""
     import torch.distributed as dist_
 
     ws, rank = dist_.get_world_size(), dist_.get_rank()
     lo, hi, per = shard_bounds(nq, ws, rank)
     idx_l, dist_l = compute_local(lo, hi)
-    idx_pad = torch.zeros((per, k), dtype=torch.int32, device=device)
-    idx_pad[: hi - lo] = idx_l
-    idx_all = torch.empty((ws * per, k), dtype=torch.int32, device=device)
-    dist_.all_gather_into_tensor(idx_all, idx_pad)
-    dist_all = None
-    if want_dist:
-        d_pad = torch.zeros((per, k), dtype=torch.float64, device=device)
-        d_pad[: hi - lo] = dist_l
-        dist_all = torch.empty((ws * per, k), dtype=torch.float64, device=device)
-        dist_.all_gather_into_tensor(dist_all, d_pad)
-        dist_all = dist_all[:nq]
-    return idx_all[:nq], dist_all
+    idx_all = all_gather_rows(idx_l.to(torch.int32), nq, per)
+    dist_all = all_gather_rows(dist_l.to(torch.float64), nq, per) if want_dist else None
+    return idx_all, dist_all
 
 
 def debug_candidates(X: torch.Tensor, Q: torch.Tensor, k: int):
@@ -182,17 +186,8 @@ def find_mutual_nn(data1: torch.Tensor, data2: torch.Tensor, k1: int, k2: int, s
     cur.wait_stream(s1); cur.wait_stream(s2)
     a.record_stream(cur); b.record_stream(cur)
 
-    def gather(local, n, k, per, lo, hi, split):
-        if not split:
-            return local
-        pad = torch.zeros((per, k), dtype=torch.int32, device=local.device)
-        pad[: hi - lo] = local
-        full = torch.empty((ws * per, k), dtype=torch.int32, device=local.device)
-        dist_.all_gather_into_tensor(full, pad)
-        return full[:n]
-
-    w21 = gather(a, n1, k2, per1, lo1, hi1, split1)
-    w12 = gather(b, n2, k1, per2, lo2, hi2, split2)
+    w21 = all_gather_rows(a, n1, per1) if split1 else a
+    w12 = all_gather_rows(b, n2, per2) if split2 else b
     first, second = find_mutual_nns(w21, w12)
     return first, second, w21, w12
 
