@@ -505,6 +505,9 @@ def _fast_mnn_core(batches, k, prop_k, restrict, ndist, merge_order, min_batch_s
         if do_correct:
             dev.center_along_batch_vector(ld, overall, left.restrict)
             dev.center_along_batch_vector(rd, overall, right.restrict)
+            if get_variance:   # recorded straight after the centring, before the tricube smoothing (R/fastMNN.R:500-501)
+                left_new = _perbatch_var(ld, left.index, left.origin)
+                right_new = _perbatch_var(rd, right.index, right.origin)
             to_add = [overall]
             re_avg, re_second = dev.average_correction(ld, rd, first, second)
             kk = min(_choose_k(k, prop_k, rd.shape[0]), re_second.shape[0])
@@ -513,9 +516,10 @@ def _fast_mnn_core(batches, k, prop_k, restrict, ndist, merge_order, min_batch_s
             rd = dev.tricube_apply(rd, re_avg, idx, dist, ndist)
         else:
             to_add = []
+            if get_variance:   # R/fastMNN.R:510-512
+                left_new = _perbatch_var(ld, left.index, left.origin)
+                right_new = _perbatch_var(rd, right.index, right.origin)
         if get_variance:
-            left_new = _perbatch_var(ld, left.index, left.origin)
-            right_new = _perbatch_var(rd, right.index, right.origin)
             var_kept[mdx, np.asarray(left.index) - 1] = left_new / left_old
             var_kept[mdx, np.asarray(right.index) - 1] = right_new / right_old
         pairings.append((first.cpu().numpy(), second.cpu().numpy()))

@@ -271,13 +271,16 @@ def reduced_mnn(batches, k=20, prop_k=None, restrict=None, ndist=3, merge_order=
         if do_correct:
             ld = center_along_batch_vector(ld, overall, left.restrict)
             rd = center_along_batch_vector(rd, overall, right.restrict)
+            # lost variance is recorded after the centring and BEFORE the tricube smoothing (R/fastMNN.R:500-501 vs :506)
+            left_new = compute_perbatch_var(ld, left.index, left.origin)
+            right_new = compute_perbatch_var(rd, right.index, right.origin)
             to_add = [overall]
             re_avg, re_second = average_correction(ld, first, rd, second)
             rd = tricube_weighted_correction(rd, re_avg, re_second, k=choose_k(k, prop_k, rd.shape[0]), ndist=ndist, knn=knn)
         else:
             to_add = []
-        left_new = compute_perbatch_var(ld, left.index, left.origin)
-        right_new = compute_perbatch_var(rd, right.index, right.origin)
+            left_new = compute_perbatch_var(ld, left.index, left.origin)     # R/fastMNN.R:510-512
+            right_new = compute_perbatch_var(rd, right.index, right.origin)
         var_kept[mdx, np.asarray(left.index) - 1] = left_new / left_old
         var_kept[mdx, np.asarray(right.index) - 1] = right_new / right_old
         pairings.append((first.astype(np.int64), second.astype(np.int64)))

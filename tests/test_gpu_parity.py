@@ -275,16 +275,37 @@ def test_smooth_gaussian_kernel_more_genes_out_than_in_and_errors():
         bb.smooth_gaussian_kernel(avg, idx + 700, mat, 0.1)
 
 
-def test_adjust_shift_variance_matches_golden(golden):
+@pytest.mark.parametrize("mode", ["fast", "exact", "cell"])
+def test_adjust_shift_variance_matches_golden(golden, mode, monkeypatch):
+    """Bit-equal to the reference object code (tests/golden/make_golden.py) in every mode: FMA-order bulk + certificate
+    (default), reference-order tiles, and the reference's loop per cell.  Identical doubles == identical quantile picks."""
+    monkeypatch.setenv("B200MNN_SHIFTVAR", mode)
     g = golden["adjust_shift_variance"]
     for s in (1.0, 0.1):
         out = bb.adjust_shift_variance(g["data1"], g["data2"], g["vect"], s, np.arange(400), np.arange(1000))
         ref = g[f"out_sigma_{s}"]
-        same = np.isclose(out, ref, rtol=1e-9, atol=1e-12)
-        print(f"sigma={s}: identical quantile picks {same.mean():.4f}, max rel err {_relerr(out, ref):.2e}")
-        assert same.mean() >= 0.999   # the discrete pick may flip on a rounding tie (the reference skips platforms over this)
+        assert np.array_equal(out, ref), f"sigma={s}: {int((out != ref).sum())} of {ref.size} cells differ, max rel err {_relerr(out, ref):.2e}"
     out = bb.adjust_shift_variance(g["data1"], g["data2"], g["vect"], 1.0, g["r1"], g["r2"])
-    assert np.isclose(out, g["out_restricted"], rtol=1e-9, atol=1e-12).mean() >= 0.999
+    assert np.array_equal(out, g["out_restricted"])
+
+
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+@pytest.mark.parametrize("n1,n2,G,sigma", [(3000, 700, 37, 0.5), (5000, 300, 130, 1.0), (700, 300, 2100, 0.1)])
+def test_adjust_shift_variance_matches_oracle_bit_exact(n1, n2, G, sigma, mode, monkeypatch):
+    """Larger shapes than the goldens: several column splits, bins of > 1 024 cells (second selection level), ragged
+    tiles, G beyond one staged chunk and beyond the old shared-memory limit -- against the C restatement (itself pinned
+    bit-identical to the reference object code in tests/test_oracle.py)."""
+    monkeypatch.setenv("B200MNN_SHIFTVAR", mode)
+    rng = np.random.default_rng(n1 + G)
+    scale = 1.0 / np.sqrt(G)
+    d1 = rng.normal(scale=scale, size=(G, n1)); d2 = rng.normal(scale=scale, size=(G, n2)) + 0.3 * scale
+    if n1 == 5000:   # a tight clump of 4 000 reference cells + a wide halo: the crossing bin overflows -> second selection level
+        d1[:, :4000] = d1[:, [0]] + 1e-4 * scale * rng.normal(size=(G, 4000))
+    cv = rng.normal(size=(n2, G))
+    r1 = rng.permutation(n1)[: n1 - 7].astype(np.int32); r2 = rng.permutation(n2)[: n2 - 5].astype(np.int32)
+    out = bb.adjust_shift_variance(d1, d2, cv, sigma, r1, r2)
+    ref = capi.adjust_shift_variance(d1, d2, cv, sigma, r1, r2)
+    assert np.array_equal(out, ref), f"{int((out != ref).sum())} of {ref.size} cells differ, max rel err {_relerr(out, ref):.2e}"
 
 
 def test_adjust_shift_variance_restrict_identity_and_zero_vector():  # test-mnn-correct.R:162-173
