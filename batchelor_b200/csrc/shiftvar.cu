@@ -182,25 +182,35 @@ sv_pairs_kernel(const double* __restrict__ grad, const double* __restrict__ data
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = 0; b < 4; ++b) { acc0[a][b] = 0.0; acc1[a][b] = 0.0; }
-        // ---- sweep 1 ----
-        for (int64_t k0 = 0; k0 < G; k0 += KC) {
-            __syncthreads();
+        // ---- sweep 1 (the next chunk's global loads are in flight while the current one is consumed) ----
+        double pg[4], pc[4], px[4];
+        auto fetch = [&](int64_t k0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t k = k0 + lk + j;
                 const bool kin = k < G;
-                Gs[lk + j][lr] = (arow >= 0 && kin) ? grad[arow * G + k] : 0.0;
-                Cs[lk + j][lr] = (arow >= 0 && kin) ? data2[arow * G + k] : 0.0;
-                Xs[lk + j][lr] = (brow >= 0 && kin) ? other[brow * G + k] : 0.0;
+                pg[j] = (arow >= 0 && kin) ? grad[arow * G + k] : 0.0;
+                pc[j] = (arow >= 0 && kin) ? data2[arow * G + k] : 0.0;
+                px[j] = (brow >= 0 && kin) ? other[brow * G + k] : 0.0;
             }
+        };
+        auto stage = [&]() {
             __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { Gs[lk + j][lr] = pg[j]; Cs[lk + j][lr] = pc[j]; Xs[lk + j][lr] = px[j]; }
+            __syncthreads();
+        };
+        fetch(0);
+        for (int64_t k0 = 0; k0 < G; k0 += KC) {
+            stage();
+            if (k0 + KC < G) fetch(k0 + KC);
             const int kmax = (int)min((int64_t)KC, G - k0);
             for (int k = 0; k < kmax; ++k) {
                 double gv[4], cv[4], xv[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) { gv[a] = Gs[k][ty * 4 + a]; cv[a] = Cs[k][ty * 4 + a]; }
 #pragma unroll
-                for (int b = 0; b < 4; ++b) xv[b] = Xs[k][tx * 4 + b];
+                for (int b = 0; b < 4; ++b) xv[b] = Xs[k][tx + 16 * b];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -223,24 +233,17 @@ sv_pairs_kernel(const double* __restrict__ grad, const double* __restrict__ data
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) dist[a][b] = 0.0;
+            fetch(0);
             for (int64_t k0 = 0; k0 < G; k0 += KC) {
-                __syncthreads();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t k = k0 + lk + j;
-                    const bool kin = k < G;
-                    Gs[lk + j][lr] = (arow >= 0 && kin) ? grad[arow * G + k] : 0.0;
-                    Cs[lk + j][lr] = (arow >= 0 && kin) ? data2[arow * G + k] : 0.0;
-                    Xs[lk + j][lr] = (brow >= 0 && kin) ? other[brow * G + k] : 0.0;
-                }
-                __syncthreads();
+                stage();
+                if (k0 + KC < G) fetch(k0 + KC);
                 const int kmax = (int)min((int64_t)KC, G - k0);
                 for (int k = 0; k < kmax; ++k) {
                     double gv[4], cv[4], xv[4];
 #pragma unroll
                     for (int a = 0; a < 4; ++a) { gv[a] = Gs[k][ty * 4 + a]; cv[a] = Cs[k][ty * 4 + a]; }
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) xv[b] = Xs[k][tx * 4 + b];
+                    for (int b = 0; b < 4; ++b) xv[b] = Xs[k][tx + 16 * b];
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -258,7 +261,7 @@ sv_pairs_kernel(const double* __restrict__ grad, const double* __restrict__ data
             // dl^2 = ||x_c||^2 + ||x||^2 - 2 x_c.x - (g.x_c - g.x)^2   
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int64_t j = cb + tx * 4 + b;
+                const int64_t j = cb + tx + 16 * b;
                 const double xn = (j < ncols) ? onorm[ridx[j]] : 0.0;
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
@@ -276,7 +279,7 @@ sv_pairs_kernel(const double* __restrict__ grad, const double* __restrict__ data
             if (cell[a] < 0) continue;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const int64_t j = cb + tx * 4 + b;
+                const int64_t j = cb + tx + 16 * b;
                 if (j >= ncols) continue;
                 if (OWN) {
                     const int64_t same = ridx[j];
