@@ -51,10 +51,12 @@ SIGNATURES = {
     "b200mnn_dev_center_along_batch_vector": [vp, i64, C.c_int, vp, vp, i64, vp],
     "b200mnn_dev_tricube_apply": [vp, i64, C.c_int, vp, i64, vp, vp, C.c_int, C.c_double, vp, vp],
     "b200mnn_dev_smooth_gaussian_kernel": [vp, i64, i64, vp, vp, i64, i64, C.c_double, vp, vp],
+    "b200mnn_smooth_last_check": [C.POINTER(C.c_int), f64p, f64p],
     "b200mnn_dev_adjust_shift_variance": [vp, i64, vp, i64, i64, vp, C.c_double, vp, i64, vp, i64, vp, vp],
     "b200mnn_dev_cosine_norm": [vp, i64, i64, vp, vp, vp],
     "b200mnn_dev_transpose_f64": [vp, i64, i64, vp, vp],
     "b200mnn_dev_debug_candidates": [vp, i64, vp, i64, C.c_int, C.c_int, vp, vp, vp, i64, i64p, vp],
+    "b200mnn_dev_debug_gemm": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp],
     "b200mnn_profile_enable": [C.c_int],
     "b200mnn_profile_collect": [f64p, i64p, f64p],
     "b200mnn_profile_collect_executed": [f64p],

@@ -151,13 +151,20 @@ int b200mnn_dev_tricube_apply(const double* d_cur, int64_t n, int d, const doubl
                               const int32_t* d_idx, const double* d_dist, int k, double ndist, double* d_out, void* stream);
 
 /* Gaussian smoothing (a5) on device: d_averaged [nmnn x G] row-major (one MNN cell contiguous), d_index0 int32[nmnn],
- * d_mat [ncells x Gdist] row-major, d_out [ncells x G]. */
+ * d_mat [ncells x Gdist] row-major, d_out [ncells x G].  Large problems run on the tensor cores (split-fp16 tcgen05 GEMMs,
+ * <= 1e-5 relative, verified per call against an fp64 re-evaluation of sampled rows; synchronises the stream), small ones
+ * in fp64 (<= 1e-10); B200MNN_SMOOTH=fp64|tensor forces one. */
 int b200mnn_dev_smooth_gaussian_kernel(const double* d_averaged, int64_t G, int64_t nmnn, const int32_t* d_index0,
                                        const double* d_mat, int64_t Gdist, int64_t ncells, double sigma2, double* d_out,
                                        void* stream);
 
+/* Which path the last smoothing call of this process took (1 = tensor cores, accepted by the fp64 sample check;
+ * 2 = fp64; 3 = tensor result rejected by the check and redone in fp64) and the check's figures: largest relative
+ * deviation of a sampled output row, largest absolute deviation of a sampled log-density. */
+int b200mnn_smooth_last_check(int* path, double* row_err, double* dens_err);
+
 /* Shift variance (a7) on device: d_data1 [n1 x G], d_data2 [n2 x G], d_vect [n2 x G] row-major; restricts 0-based
- * device int32; d_out double[n2]. */
+ * device int32; d_out double[n2].  Synchronises the stream (restrict validation, operand scale). */
 int b200mnn_dev_adjust_shift_variance(const double* d_data1, int64_t n1, const double* d_data2, int64_t n2, int64_t G,
                                       const double* d_vect, double sigma2, const int32_t* d_r1, int64_t nr1,
                                       const int32_t* d_r2, int64_t nr2, double* d_out, void* stream);
@@ -174,6 +181,13 @@ int b200mnn_dev_transpose_f64(const double* d_in, int64_t rows, int64_t cols, do
 int b200mnn_dev_debug_candidates(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k,
                                  int32_t* d_cand_idx, double* d_cand_d2, double* d_thr, int64_t cand_capacity,
                                  int64_t* ncand_out, void* stream);
+
+/* Debug/validation hook for tests: out[M x ldo] (fp32, ldo a multiple of 256 and >= N rounded up to 256) =
+ * A[M x K] . B[N x K]^T (fp64 row-major device matrices) through the split-fp16 tcgen05 GEMM that the gene-space kernels
+ * (Gaussian smoothing, wide-d kNN) are built on.  terms: 3 = Ah.Bh + Al.Bh + Ah.Bl, 1 = Ah.Bh; chunk_boxes: K boxes (64
+ * columns) per TMEM accumulation chain (<= 0: one chain).  Synchronises once (operand scale). */
+int b200mnn_dev_debug_gemm(const double* dA, int64_t M, const double* dB, int64_t N, int64_t K, int terms, int chunk_boxes,
+                           float* d_out, int64_t ldo, void* stream);
 
 /* Measurement hook (bench.py's roofline figure): while enabled, CUDA events are recorded on the launch stream around
  * every launch of the dominant kernel (the tcgen05 candidate-scoring kernel).  b200mnn_profile_collect synchronises

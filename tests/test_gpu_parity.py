@@ -265,6 +265,48 @@ def test_smooth_gaussian_kernel_matches_golden(golden, case):
     assert _relerr(out, g[f"{case}_out"]) < 1e-10
 
 
+def _smooth_path():
+    import ctypes as C
+    from batchelor_b200 import _lib
+    path, e0, e1 = C.c_int(0), C.c_double(0), C.c_double(0)
+    _lib.call("b200mnn_smooth_last_check", C.byref(path), C.byref(e0), C.byref(e1))
+    return path.value, e0.value, e1.value
+
+
+@pytest.mark.parametrize("case", ["vanilla", "repeated", "many", "wide"])
+def test_smooth_gaussian_kernel_tensor_path_matches_golden(golden, case, monkeypatch):
+    """The tcgen05 path (forced here; by default only large problems take it) against the reference object code: 1e-5."""
+    monkeypatch.setenv("B200MNN_SMOOTH", "tensor")
+    g = golden["smooth_gaussian_kernel"]
+    out = bb.smooth_gaussian_kernel(g[f"{case}_averaged"], g[f"{case}_index0"], g["data2"].T, float(g[f"{case}_sigma"]))
+    path, e0, e1 = _smooth_path()
+    err = _relerr(out, g[f"{case}_out"])
+    print(f"{case}: path {path}, rel err {err:.2e}, in-call sample check rows {e0:.2e} log-density {e1:.2e}")
+    assert path == 1 and err < RTOL
+
+
+@pytest.mark.parametrize("ncells,nmnn,Gd,G,sigma,normalise", [(6000, 1500, 300, 300, 0.1, True), (3000, 700, 2000, 2100, 0.1, True),
+                                                              (2500, 900, 130, 64, 1.0, False)])
+def test_smooth_gaussian_kernel_tensor_path_matches_oracle(ncells, nmnn, Gd, G, sigma, normalise, monkeypatch):
+    """Mid-size shapes (several tiles, ragged edges, G != Gdist, K-chunked accumulation) against the fp64 C restatement."""
+    monkeypatch.setenv("B200MNN_SMOOTH", "tensor")
+    rng = np.random.default_rng(ncells + G)
+    centres = rng.normal(size=(5, Gd))
+    mat = (centres[rng.integers(0, 5, size=ncells)] * 0.15 + rng.normal(size=(ncells, Gd))).T
+    if normalise:
+        mat = mat / np.linalg.norm(mat, axis=0, keepdims=True)
+    else:
+        mat *= 0.1
+    idx = np.sort(rng.permutation(ncells)[:nmnn]).astype(np.int32)
+    avg = rng.normal(size=(G, nmnn)) * 0.05 + 0.02
+    out = bb.smooth_gaussian_kernel(avg, idx, mat, sigma)
+    path, e0, e1 = _smooth_path()
+    ref = capi.smooth_gaussian_kernel(avg, idx, mat, sigma)
+    err = _relerr(out, ref)
+    print(f"path {path}, rel err {err:.2e}, in-call sample check rows {e0:.2e} log-density {e1:.2e}")
+    assert path == 1 and err < RTOL
+
+
 def test_smooth_gaussian_kernel_more_genes_out_than_in_and_errors():
     rng = np.random.default_rng(8)
     mat = rng.normal(scale=0.1, size=(30, 700)); avg = rng.normal(size=(90, 64)); idx = rng.permutation(700)[:64].astype(np.int32)
@@ -472,3 +514,27 @@ def test_results_are_deterministic_run_to_run():
     a = bb.reducedMNN(b1, b2, k=20); b = bb.reducedMNN(b1, b2, k=20)
     assert np.array_equal(a.corrected, b.corrected)
     assert np.array_equal(a.merge_info["pairs"][0]["left"], b.merge_info["pairs"][0]["left"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# split-fp16 tcgen05 GEMM (engine of the gene-space kernels) against fp64 matmul
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,terms,cb", [(128, 256, 64, 3, 0), (300, 700, 200, 3, 2), (129, 257, 1000, 3, 8), (1500, 3000, 2000, 3, 8),
+                                           (300, 700, 200, 1, 0), (2100, 1030, 130, 1, 1)])
+def test_split_gemm_matches_fp64(M, N, K, terms, cb):
+    import ctypes as C
+    import torch
+    from batchelor_b200 import _lib
+    rng = np.random.default_rng(M + N + K)
+    A = rng.normal(size=(M, K)) * 3.0 + 0.5; B = rng.normal(size=(N, K)) * 0.02
+    dA = torch.from_numpy(A).cuda(); dB = torch.from_numpy(B).cuda()
+    ldo = (N + 255) // 256 * 256
+    out = torch.full((M, ldo), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.call("b200mnn_dev_debug_gemm", C.c_void_p(dA.data_ptr()), M, C.c_void_p(dB.data_ptr()), N, K, terms, cb, C.c_void_p(out.data_ptr()), ldo,
+              C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    got = out[:, :N].double().cpu().numpy()
+    ref = A @ B.T
+    scale = np.linalg.norm(A, axis=1)[:, None] * np.linalg.norm(B, axis=1)[None, :]
+    err = np.max(np.abs(got - ref) / scale)
+    print(f"max |err| / (|a||b|) = {err:.3e}")
+    assert err < (2e-6 if terms == 3 else 2e-3)
