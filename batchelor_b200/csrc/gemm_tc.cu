@@ -202,12 +202,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constan
                 for (int j = 0; j < 32; ++j)
                     orow[j] = make_float4(acc[4 * j] * al, acc[4 * j + 1] * al, acc[4 * j + 2] * al, acc[4 * j + 3] * al);
             } else if (EPI == EPI_SCORE) {
+                const float al = (float)ep.alpha;   // a power of two: the product is exact, one rounding in the add
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float cv[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { const int64_t cc = cbase + 4 * j + i; cv[i] = (cc < ep.N) ? ep.colf[cc] : __int_as_float(0x7f800000); }
-                    orow[j] = make_float4(cv[0] + acc[4 * j], cv[1] + acc[4 * j + 1], cv[2] + acc[4 * j + 2], cv[3] + acc[4 * j + 3]);
+                    orow[j] = make_float4(fmaf(al, acc[4 * j], cv[0]), fmaf(al, acc[4 * j + 1], cv[1]), fmaf(al, acc[4 * j + 2], cv[2]),
+                                          fmaf(al, acc[4 * j + 3], cv[3]));
                 }
             } else {
                 const double rd = ep.rowd[row];

@@ -27,7 +27,7 @@ static inline int64_t pad_k(int64_t K) { return round_up(K < 1 ? 1 : K, KBOX); }
 
 enum Epilogue : int {
     EPI_PLAIN = 0,   // out = alpha * acc
-    EPI_SCORE = 1,   // out = colf[c] + acc                                   (kNN score S^2 (||x||^2 - 2 q.x))
+    EPI_SCORE = 1,   // out = colf[c] + alpha * acc                           (kNN score S^2 (||x||^2 - 2 q.x), alpha = -2)
     EPI_LOGIT = 2,   // out = (beta * acc - rowd[r] - cold[c]) * inv_sigma - dens[c]   (Gaussian log-weight minus log-density)
 };
 

@@ -11,6 +11,16 @@ struct DebugOut;
 bool tensor_path_supported(int64_t n, int64_t nq, int d, int k);
 int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
                      int64_t* d_stats, cudaStream_t stream, const DebugOut* dbg);
+// knn_wide.cu: K-streamed tensor-core path for wide data / large k
+bool wide_path_supported(int64_t n, int64_t nq, int d, int k);
+int query_knn_wide(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
+                   int64_t* d_stats, cudaStream_t stream);
+// knn_tc.cu: exact fp64 scan of the flagged queries (flag_dk2: exact squared distance of each one's k-th candidate), or of all
+int launch_rescue(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, const int* flag_count, const int32_t* flag_list,
+                  const double* flag_dk2, int32_t* d_idx, double* d_dist, cudaStream_t stream);
+int launch_rescue_all(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
+                      int64_t* d_stats, cudaStream_t stream);
+int write_stats(const int* flag_count, int64_t* d_stats, int64_t lists, int64_t path, cudaStream_t stream);
 }  // namespace knn
 
 namespace mutual {

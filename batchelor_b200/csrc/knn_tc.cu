@@ -25,6 +25,7 @@
 //                       the generic path for shapes the tensor path does not cover (k > 56, d > ~190).
 #include "common.cuh"
 #include "knn_cluster.cuh"
+#include "internal.cuh"
 #include "tc_ptx.cuh"
 
 #include <cuda.h>
@@ -1527,7 +1528,7 @@ constexpr int RS_CAP = 1024;   // references a block can collect in its single-p
 __global__ void __launch_bounds__(RS_THREADS)
 rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Q, int d, int k,
               const int* __restrict__ flag_count, const int32_t* __restrict__ flag_list, const double* __restrict__ flag_dk2, int64_t nq_all,
-              int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+              int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const int use_smem) {
     __shared__ double sd[RS_THREADS / 32];
     __shared__ int si[RS_THREADS / 32];
     __shared__ double pick_d;
@@ -1535,12 +1536,14 @@ rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict_
     __shared__ double col_d[RS_CAP];
     __shared__ int col_i[RS_CAP];
     __shared__ int col_n;
-    extern __shared__ double qs[];  // [d]
+    extern __shared__ double qs_sm[];  // [d] when use_smem
     const int count = flag_list ? *flag_count : (int)nq_all;
     for (int f = blockIdx.x; f < count; f += gridDim.x) {
         const int64_t q = flag_list ? flag_list[f] : f;
         __syncthreads();
-        for (int t = threadIdx.x; t < d; t += blockDim.x) qs[t] = Q[q * d + t];
+        const double* qs = use_smem ? qs_sm : Q + q * d;   // very wide rows are read through L1 instead
+        if (use_smem)
+            for (int t = threadIdx.x; t < d; t += blockDim.x) qs_sm[t] = Q[q * d + t];
         if (threadIdx.x == 0) { pick_d = -1.0; pick_i = -1; col_n = 0; }
         __syncthreads();
         // single-pass collection of everything within the bound
@@ -1762,6 +1765,49 @@ struct DebugOut {
     int64_t* ncand_host = nullptr;
 };
 
+// The query row is staged in shared memory when it fits next to the kernel's static buffers (opt-in up to the device
+// limit); wider rows are read from global memory.
+static int rescue_smem(int d, int* use_smem, size_t* bytes) {
+    int dev = 0, max_smem = 0;
+    B200_CUDA(cudaGetDevice(&dev));
+    B200_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t need = (size_t)std::max(d, 1) * sizeof(double);
+    const size_t room = (size_t)max_smem > (size_t)16 * 1024 ? (size_t)max_smem - 16 * 1024 : 0;   // static: col_d, col_i, reductions
+    *use_smem = need <= room ? 1 : 0;
+    *bytes = *use_smem ? need : 0;
+    if (*use_smem && need > 32 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(rescue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    return 0;
+}
+
+int launch_rescue(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, const int* flag_count, const int32_t* flag_list,
+                  const double* flag_dk2, int32_t* d_idx, double* d_dist, cudaStream_t stream) {
+    int use_smem = 0;
+    size_t bytes = 0;
+    B200_TRY(rescue_smem(d, &use_smem, &bytes));
+    rescue_kernel<<<sm_count() * 4, RS_THREADS, bytes, stream>>>(dX, n, dQ, d, k, flag_count, flag_list, flag_dk2, nq, d_idx, d_dist, use_smem);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_rescue_all(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
+                      int64_t* d_stats, cudaStream_t stream) {
+    int use_smem = 0;
+    size_t bytes = 0;
+    B200_TRY(rescue_smem(d, &use_smem, &bytes));
+    const int grid = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 8);
+    rescue_kernel<<<grid, RS_THREADS, bytes, stream>>>(dX, n, dQ, d, k, nullptr, nullptr, nullptr, nq, d_idx, d_dist, use_smem);
+    B200_LAUNCH_CHECK();
+    if (d_stats) { write_stats_kernel<<<1, 1, 0, stream>>>(nullptr, d_stats, 0, 0); B200_LAUNCH_CHECK(); }
+    return 0;
+}
+
+int write_stats(const int* flag_count, int64_t* d_stats, int64_t lists, int64_t path, cudaStream_t stream) {
+    write_stats_kernel<<<1, 1, 0, stream>>>(flag_count, d_stats, lists, path);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
 int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
                      int64_t* d_stats, cudaStream_t stream, const DebugOut* dbg) {
     B200_TRY(ensure_device());
@@ -1773,12 +1819,11 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
 
     if (!tensor_path_supported(n, nq, d, k) || d == 0) {
         if (dbg) return fail(B200MNN_EINVAL, "debug candidates requested for a shape outside the tensor path");
-        // generic exact path: every query through the rescue kernel
-        const int grid = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 8);
-        rescue_kernel<<<grid, RS_THREADS, (size_t)std::max(d, 1) * sizeof(double), stream>>>(dX, n, dQ, d, k, nullptr, nullptr, nullptr, nq, d_idx, d_dist);
-        B200_LAUNCH_CHECK();
-        if (d_stats) { write_stats_kernel<<<1, 1, 0, stream>>>(nullptr, d_stats, 0, 0); B200_LAUNCH_CHECK(); }
-        return 0;
+        // wide rows (gene space) or large k: K-streamed tensor-core scoring + selection (knn_wide.cu); B200MNN_WIDE=0 forces
+        // the generic exact scan, which is also what remains for k beyond the candidate capacity
+        const char* wenv = getenv("B200MNN_WIDE");
+        if (d > 0 && wide_path_supported(n, nq, d, k) && !(wenv && atoi(wenv) == 0)) return query_knn_wide(dX, n, dQ, nq, d, k, d_idx, d_dist, d_stats, stream);
+        return launch_rescue_all(dX, n, dQ, nq, d, k, d_idx, d_dist, d_stats, stream);
     }
 
     const KLayout L = make_layout(d);
@@ -2081,8 +2126,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         rescue_count = flag_count2;
         rescue_list = flag_list2;
     }
-    rescue_kernel<<<sm_count() * 4, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, k, rescue_count, rescue_list, flag_dk2, nq, d_idx, d_dist);
-    B200_LAUNCH_CHECK();
+    B200_TRY(launch_rescue(dX, n, dQ, nq, d, k, rescue_count, rescue_list, flag_dk2, d_idx, d_dist, stream));
     if (d_stats) {
         write_stats_kernel<<<1, 1, 0, stream>>>(rescue_count, d_stats, nsplit, use_prune ? 2 : 1, two_tier ? flag_count : nullptr, use_ts ? visited : nullptr,
                                                 ceil_div(nq, BM) * ceil_div(n, TS_BN));

@@ -36,6 +36,10 @@ def _relerr(a, b):
     (1500, 400, 32, 10), (1500, 400, 64, 10), (1500, 400, 100, 10), (800, 200, 192, 10),
     (800, 200, 250, 10),      # d beyond the resident-operand kernel -> generic exact path
     (40, 100, 50, 40),        # k = n
+    # wide rows / large k: K-streamed tensor-core scoring + radix selection (csrc/knn_wide.cu)
+    (3000, 1000, 512, 20), (2500, 700, 2000, 20), (3000, 500, 50, 100), (3000, 300, 50, 1000), (1300, 300, 333, 57),
+    (700, 200, 6000, 10),     # a row wider than the rescue kernel's former shared-memory staging
+    (3000, 64, 30, 1400),     # k beyond the candidate capacity -> generic exact scan
 ])
 def test_query_knn_matches_oracle_bit_exact(n, nq, d, k):
     X, Q = synth.pc_batches(2, [n, nq], d=d, ncomp=8)
@@ -538,3 +542,19 @@ def test_split_gemm_matches_fp64(M, N, K, terms, cb):
     err = np.max(np.abs(got - ref) / scale)
     print(f"max |err| / (|a||b|) = {err:.3e}")
     assert err < (2e-6 if terms == 3 else 2e-3)
+
+
+def test_query_knn_wide_path_ties_and_gene_space():
+    """Wide path: integer grid (massive exact ties across the selection threshold -> rescue) and cosine-normalised gene-space
+    data as mnnCorrect searches it (R/mnnCorrect.R:288-289)."""
+    rng = np.random.default_rng(5)
+    X = rng.integers(0, 2, size=(1500, 300)).astype(np.float64); Q = rng.integers(0, 2, size=(400, 300)).astype(np.float64)
+    X[100:140] = X[7]   # 41 identical references: more ties than any candidate margin absorbs
+    got = bb.queryKNN(X, Q, 20)
+    idx, dist = capi.query_knn(X, Q, 20)
+    assert np.array_equal(got["index"], idx) and np.array_equal(got["distance"], dist)
+    A, B = synth.gene_batches(2, [2600, 2200], G=2000)
+    A = A / np.linalg.norm(A, axis=0); B = B / np.linalg.norm(B, axis=0)
+    got = bb.findMutualNN(A.T, B.T, k1=20, k2=20)
+    f, s = capi.find_mutual_nn(np.ascontiguousarray(A.T), np.ascontiguousarray(B.T), 20, 20)
+    assert np.array_equal(got["first"], f) and np.array_equal(got["second"], s)
