@@ -57,6 +57,8 @@ SIGNATURES = {
     "b200mnn_dev_transpose_f64": [vp, i64, i64, vp, vp],
     "b200mnn_dev_debug_candidates": [vp, i64, vp, i64, C.c_int, C.c_int, vp, vp, vp, i64, i64p, vp],
     "b200mnn_dev_debug_gemm": [vp, i64, vp, i64, i64, C.c_int, C.c_int, vp, i64, vp],
+    "b200mnn_gemm_profile_enable": [C.c_int],
+    "b200mnn_gemm_profile_collect": [f64p, i64p, f64p],
     "b200mnn_profile_enable": [C.c_int],
     "b200mnn_profile_collect": [f64p, i64p, f64p],
     "b200mnn_profile_collect_executed": [f64p],

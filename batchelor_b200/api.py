@@ -589,9 +589,21 @@ def fastMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, cos_norm=Tru
 # ----------------------------------------------------------------------------------------------------------
 def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1, cos_norm_in=True, cos_norm_out=True,
                svd_dim=0, var_adj=True, subset_row=None, correct_all=False, merge_order=None, auto_merge=False,
-               BNPARAM=None, BPPARAM=None) -> MNNResult:
-    """mnnCorrect for [genes x cells] matrices; ``corrected`` is [genes x cells] in the input batch order."""
+               BNPARAM=None, BPPARAM=None, _timings=None) -> MNNResult:
+    """mnnCorrect for [genes x cells] matrices; ``corrected`` is [genes x cells] in the input batch order.
+
+    ``_timings`` (measurement aid, not part of the reference's signature): a dict that receives the seconds spent per
+    stage (upload, cosine norm, MNN search, averaging, smoothing, shift variance, download), each bracketed by a
+    device synchronisation."""
+    import time
+
     import torch
+
+    def _tick(name, t0):
+        if _timings is not None:
+            torch.cuda.synchronize()
+            _timings[name] = _timings.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
 
     from . import device as dev
 
@@ -616,8 +628,11 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
     dev.require_cuda()
     cuda = torch.device("cuda", torch.cuda.current_device())
 
-    # .prepare_input_data (R/mnnCorrect.R:398-442); device layout is [cells x genes]
-    raw = [torch.from_numpy(np.ascontiguousarray(m.T)).to(cuda) for m in mats]
+    # .prepare_input_data (R/mnnCorrect.R:398-442); device layout is [cells x genes]: R's column-major [genes x cells]
+    # IS that layout, so a Fortran-ordered input uploads without any host-side transpose
+    t0 = time.perf_counter()
+    raw = [torch.from_numpy(m.T if m.flags.f_contiguous else np.ascontiguousarray(m.T)).to(cuda) for m in mats]
+    t0 = _tick("upload", t0)
     sub = None
     if subset_row is not None:
         sidx = _subset_to_index(subset_row, G)
@@ -645,6 +660,7 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
     if cos_norm_out != cos_norm_in:
         same_set = False
 
+    t0 = _tick("cosine_norm", t0)
     nb = len(mats)
     tree = _predefined_tree(nb, merge_order)
 
@@ -660,16 +676,25 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
         left, right, path = _next_merge(tree)
         ld, rd = left.data, right.data
         lx, rx = left.extras[0], right.extras[0]
+        t0 = time.perf_counter()
         s1, s2 = _restricted_mnn(dev, ld, left.restrict, rd, right.restrict, k, prop_k)
         if s1.numel() == 0:
             raise B200Error(1, "no MNN pairs found between the batches being merged")
         pairings.append((s1.cpu().numpy(), s2.cpu().numpy()))
+        t0 = _tick("mnn_search", t0)
         left_set.append(list(left.index)); right_set.append(list(right.index))
 
         def correction(d1, d2, adjust_sub):
             # .compute_correction_vectors (R/mnnCorrect.R:451-460): distances always in the *input* space (rd)
+            tc = time.perf_counter()
             averaged, uniq = dev.average_correction(d1, d2, s1, s2)
+            tc = _tick("average_correction", tc)
+            if _timings is not None:
+                _timings["mnn_cells"] = int(uniq.shape[0])
             cor = dev.smooth_gaussian_kernel(averaged, uniq, rd, sigma)
+            tc = _tick("smooth_gaussian_kernel", tc)
+            if _timings is not None:
+                _timings.setdefault("_smooth_io", []).append((averaged, uniq, rd, cor))
             if var_adj:  # .adjust_shift_variance (R/mnnCorrect.R:462-481)
                 r1 = left.restrict if left.restrict is not None else torch.arange(d1.shape[0], device=cuda)
                 r2 = right.restrict if right.restrict is not None else torch.arange(d2.shape[0], device=cuda)
@@ -678,7 +703,10 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
                                                         cor.index_select(1, adjust_sub).contiguous(), sigma, r1, r2)
                 else:
                     scaling = dev.adjust_shift_variance(d1, d2, cor, sigma, r1, r2)
+                if _timings is not None:   # what a sampled parity check of this stage needs: its inputs and its output
+                    _timings.setdefault("_shiftvar_io", []).append((d1, d2, cor, r1, r2, scaling))
                 cor = torch.clamp(scaling, min=1.0)[:, None] * cor  # pmax(scaling, 1) * correction
+                tc = _tick("adjust_shift_variance", tc)
             return cor
 
         cor_in = correction(ld, rd, None)
@@ -691,9 +719,11 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
                      origin=np.concatenate([left.origin, right.origin]),
                      extras=[None if same_set else torch.cat([lx, new_rx], dim=0)])
         tree = _update(tree, path, node)
+    t0 = time.perf_counter()
     full = (tree.data if same_set else tree.extras[0]).cpu().numpy()
     res = _finish(tree, full, pairings, left_set, right_set, {})
-    res.corrected = np.ascontiguousarray(res.corrected.T)
+    res.corrected = res.corrected.T   # [genes x cells], Fortran-ordered like an R matrix: no host-side transpose
+    t0 = _tick("download", t0)
     if do_split:
         res.corrected = res.corrected[:, reorder - 1]
         res.batch = res.batch[reorder - 1]

@@ -550,3 +550,8 @@ extern "C" int b200mnn_dev_debug_gemm(const double* dA, int64_t M, const double*
     ep.alpha = scalbn(1.0, -(ea + eb));
     return gemm_split(A, B, terms, EPI_PLAIN, ep, chunk_boxes, stream);
 }
+
+extern "C" int b200mnn_gemm_profile_enable(int on) { return b200::gemm::profile_enable(on); }
+extern "C" int b200mnn_gemm_profile_collect(double* total_ms, int64_t* launches, double* executed_flops) {
+    return b200::gemm::profile_collect(total_ms, launches, executed_flops);
+}

@@ -103,6 +103,22 @@ def all_gather_rows(local: torch.Tensor, n: int, per: int) -> torch.Tensor:
     return full[:n]
 
 
+def upload_sharded(host: torch.Tensor, device) -> torch.Tensor:
+    """Host matrix -> replicated device matrix, paying the PCIe transfer once per row instead of once per rank: every rank
+    copies only its contiguous block of rows (:func:`shard_bounds`) and the blocks are all-gathered over NVLink.  `host`
+    must hold the same data on every rank (pinned memory makes the copy asynchronous).  Without a process group this is a
+    plain upload."""
+    import torch.distributed as dist_
+
+    if not (dist_.is_available() and dist_.is_initialized()) or dist_.get_world_size() == 1:
+        return host.to(device, non_blocking=True)
+    ws, rank = dist_.get_world_size(), dist_.get_rank()
+    n = host.shape[0]
+    lo, hi, per = shard_bounds(n, ws, rank)
+    local = host[lo:hi].to(device, non_blocking=True)
+    return all_gather_rows(local, n, per)
+
+
 def shard_rows_and_gather(nq: int, k: int, compute_local, device, want_dist: bool = True):
     """Host-side sharding logic: every rank computes `compute_local(lo, hi) -> (idx[hi-lo, k], dist or None)` for its
     contiguous block of rows (:func:`shard_bounds`); the blocks are exchanged with :func:`all_gather_rows`, so every rank

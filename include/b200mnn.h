@@ -199,6 +199,11 @@ int b200mnn_profile_collect(double* total_ms, int64_t* launches, double* algorit
  * scoring tier adds some): issued tcgen05.mma instructions x 2*128*128*16. */
 int b200mnn_profile_collect_executed(double* executed_flops);
 
+/* Same for the split-fp16 tcgen05 GEMM launches of the gene-space kernels (smoothing, wide-d kNN): summed CUDA-event
+ * time, launches and EXECUTED tensor flops (terms x padded tiles x K). */
+int b200mnn_gemm_profile_enable(int on);
+int b200mnn_gemm_profile_collect(double* total_ms, int64_t* launches, double* executed_flops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,8 +26,9 @@ _i64, _i32p, _f64p = C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_double)
 
 def build(force: bool = False) -> None:
     """Compile both checkers (the reference one only when /root/reference is present)."""
-    if force or not os.path.exists(_ORACLE_SO):
-        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    if force and os.path.exists(_ORACLE_SO):
+        os.remove(_ORACLE_SO)
+    subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)   # no-op when up to date
     if os.path.isdir("/root/reference/src") and (force or not os.path.exists(_REF_SO)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
@@ -210,6 +211,25 @@ def adjust_shift_variance(data1, data2, vect, sigma2, restrict1, restrict2, nthr
         raise OracleError("subset indices out of range")
     if rc:
         raise OracleError(f"adjust_shift_variance rc={rc}")
+    return out
+
+
+def adjust_shift_variance_cells(data1, data2, vect_rows, cells, sigma2, restrict1, restrict2, nthreads=0):
+    """Scaling of the requested batch-2 cells only (same per-cell loop): data1 [G x n1], data2 [G x n2] column-major,
+    vect_rows [len(cells) x G] = the correction rows of those cells."""
+    D1 = _f64(data1); D2 = _f64(data2); r1 = _i32(restrict1); r2 = _i32(restrict2)
+    V = np.ascontiguousarray(np.asarray(vect_rows, dtype=np.float64))
+    cells = np.ascontiguousarray(np.asarray(cells, dtype=np.int64))
+    out = np.zeros(cells.size, dtype=np.float64)
+    fn = lib().oracle_adjust_shift_variance_cells
+    fn.restype = C.c_int
+    fn.argtypes = [_f64p, C.c_int64, C.c_int64, _f64p, C.c_int64, C.c_int64, _f64p, C.c_int64, C.c_int64, C.c_double, _i32p, C.c_int64,
+                   _i32p, C.c_int64, C.POINTER(C.c_int64), C.c_int64, C.c_int, _f64p, C.c_int]
+    rc = fn(_p(D1, _f64p), D1.shape[0], D1.shape[1], _p(D2, _f64p), D2.shape[0], D2.shape[1], V.ctypes.data_as(_f64p), D2.shape[1], D1.shape[0],
+            float(sigma2), _p(r1, _i32p), r1.size, _p(r2, _i32p), r2.size, cells.ctypes.data_as(C.POINTER(C.c_int64)), cells.size, 1,
+            out.ctypes.data_as(_f64p), nthreads)
+    if rc:
+        raise OracleError(f"adjust_shift_variance_cells rc={rc}")
     return out
 
 

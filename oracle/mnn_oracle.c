@@ -239,10 +239,13 @@ static double sqdist_to_line(const double* ref, const double* grad, const double
     return dist;
 }
 
-int oracle_adjust_shift_variance(const double* data1, int64_t G1, int64_t n1, const double* data2, int64_t G2, int64_t n2,
-                                 const double* vect, int64_t vr, int64_t vc, double sigma2,
-                                 const int32_t* r1, int64_t nr1, const int32_t* r2, int64_t nr2, double* out,
-                                 int nthreads) {
+/* `cells` (may be NULL = every cell of batch 2): the cells whose scaling is wanted; out[i] belongs to cells[i].  The
+ * subset form exists so that tests can check sampled cells of a problem whose full O(n2 (n1 + n2) G) loop would take
+ * days on a CPU; the arithmetic per cell is the same loop. */
+int oracle_adjust_shift_variance_cells(const double* data1, int64_t G1, int64_t n1, const double* data2, int64_t G2, int64_t n2,
+                                       const double* vect, int64_t vr, int64_t vc, double sigma2,
+                                       const int32_t* r1, int64_t nr1, const int32_t* r2, int64_t nr2,
+                                       const int64_t* cells, int64_t ncells_sub, int vect_rows_are_cells, double* out, int nthreads) {
     const int64_t G = G1;
     if (G != G2 || G != vc) return 1;
     if (n2 != vr) return 4;
@@ -258,11 +261,14 @@ int oracle_adjust_shift_variance(const double* data1, int64_t G1, int64_t n1, co
         double* work = (double*)malloc(sizeof(double) * (size_t)(G > 0 ? G : 1));
         double* grad = (double*)malloc(sizeof(double) * (size_t)(G > 0 ? G : 1));
         pl_t* d1 = (pl_t*)malloc(sizeof(pl_t) * (size_t)(nr1 > 0 ? nr1 : 1));
-#pragma omp for schedule(dynamic, 4)
-        for (int64_t c = 0; c < n2; ++c) {
+        const int64_t ncount = cells ? ncells_sub : n2;
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t ci = 0; ci < ncount; ++ci) {
+            const int64_t c = cells ? cells[ci] : ci;
             const double* cur = data2 + c * G;
             double l2 = 0.0;
-            for (int64_t g = 0; g < G; ++g) { grad[g] = vect[c + g * n2]; l2 += grad[g] * grad[g]; }
+            /* vect is [n2 x G] column-major as in R, or (subset form) one contiguous G-vector per requested cell */
+            for (int64_t g = 0; g < G; ++g) { grad[g] = vect_rows_are_cells ? vect[ci * G + g] : vect[c + g * n2]; l2 += grad[g] * grad[g]; }
             l2 = sqrt(l2);
             if (l2 != 0.0) for (int64_t g = 0; g < G; ++g) grad[g] /= l2;
             double curproj = 0.0;
@@ -309,11 +315,18 @@ int oracle_adjust_shift_variance(const double* data1, int64_t G1, int64_t n1, co
                     if (cum >= target) { refq = d1[o].proj; break; }
                 }
             }
-            out[c] = (refq - curproj) / l2;
+            out[cells ? ci : c] = (refq - curproj) / l2;
         }
         free(work); free(grad); free(d1);
     }
     return 0;
+}
+
+int oracle_adjust_shift_variance(const double* data1, int64_t G1, int64_t n1, const double* data2, int64_t G2, int64_t n2,
+                                 const double* vect, int64_t vr, int64_t vc, double sigma2,
+                                 const int32_t* r1, int64_t nr1, const int32_t* r2, int64_t nr2, double* out,
+                                 int nthreads) {
+    return oracle_adjust_shift_variance_cells(data1, G1, n1, data2, G2, n2, vect, vr, vc, sigma2, r1, nr1, r2, nr2, NULL, 0, 0, out, nthreads);
 }
 
 /* a9. cosine normalisation, R/cosineNorm.R:53-82: l2 = sqrt(colSums(x^2)); x / max(1e-8, l2).

@@ -267,3 +267,24 @@ def test_mnn_correct_oracle_runs_and_restrict_identity():  # test-mnn-correct.R:
     r = ref["corrected"]; o = out["corrected"]
     assert np.array_equal(r[:, :60], o[:, :60]) and np.array_equal(r[:, 60:], o[:, 71:151])
     assert np.array_equal(r[:, 60:][:, i2 - 1], o[:, 151:])
+
+
+def test_shift_variance_cell_subset_equals_full_loop(golden):
+    """The subset form used to check sampled cells of problems too large for a full CPU pass is the same per-cell loop."""
+    g = golden["adjust_shift_variance"]
+    cells = np.array([0, 7, 500, 999, 3], dtype=np.int64)
+    sub = capi.adjust_shift_variance_cells(g["data1"], g["data2"], g["vect"][cells], cells, 0.1, np.arange(400), np.arange(1000))
+    assert np.array_equal(sub, g["out_sigma_0.1"][cells])
+
+
+def test_lost_var_is_recorded_before_the_tricube_step():
+    """R/fastMNN.R:500-501 records the variance right after the centring along the batch vector.  Hand computation: the
+    centring removes exactly the variance of the projections on the unit batch vector (no restriction, first merge)."""
+    rng = np.random.default_rng(11)
+    b1 = rng.normal(size=(300, 10)); b2 = rng.normal(size=(250, 10)) + 2.0
+    res = ho.reduced_mnn([b1, b2], k=15)
+    first, second = ho.restricted_mnn(b1, None, b2, None, 15)
+    averaged, _ = ho.average_correction(b1, first, b2, second)
+    v = averaged.mean(axis=0); v /= np.linalg.norm(v)
+    want = [np.var(X @ v, ddof=1) / np.var(X, axis=0, ddof=1).sum() for X in (b1, b2)]
+    assert np.allclose(res["merge_info"]["lost_var"][0], want, rtol=1e-9, atol=1e-12)
