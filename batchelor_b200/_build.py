@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(LIBDIR, "libb200mnn.so")
-SOURCES = ["common.cu", "scan.cu", "gemm_tc.cu", "knn_tc.cu", "knn_wide.cu", "knn_cluster.cu", "mutual.cu", "correct.cu", "smooth.cu", "shiftvar.cu", "capi.cu"]
+SOURCES = ["common.cu", "scan.cu", "gemm_tc.cu", "knn_tc.cu", "knn_wide.cu", "knn_cluster.cu", "mutual.cu", "correct.cu", "smooth.cu", "shiftvar.cu", "merge.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -44,6 +44,15 @@ SIGNATURES = {
     "b200mnn_average_correction": [f64p, i64, f64p, i64, C.c_int, i32p, i32p, i64, f64p, i32p, i64p],
     "b200mnn_center_along_batch_vector": [f64p, i64, C.c_int, f64p, i32p, i64, f64p],
     "b200mnn_tricube_weighted_correction": [f64p, i64, C.c_int, f64p, i32p, i64, C.c_int, C.c_double, f64p],
+    "b200mnn_reduced_mnn": [C.POINTER(f64p), i64p, C.c_int, C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_double, C.c_double, C.c_double,
+                            C.POINTER(i32p), i64p, C.c_int, C.POINTER(vp)],
+    "b200mnn_result_ncells": [vp],
+    "b200mnn_result_npairs": [vp, C.c_int],
+    "b200mnn_result_pairs": [vp, C.c_int, i32p, i32p],
+    "b200mnn_result_corrected": [vp, f64p, C.c_int],
+    "b200mnn_result_info": [vp, i32p, i64p, f64p, i32p, f64p],
+    "b200mnn_result_merges": [vp, i32p, i32p],
+    "b200mnn_result_free": [vp],
     # device-pointer entry points: raw addresses (void*) so torch tensors' data_ptr() can be passed directly
     "b200mnn_dev_query_knn": [vp, i64, vp, i64, C.c_int, C.c_int, vp, vp, vp, vp],
     "b200mnn_dev_find_mutual_nns": [vp, i64, C.c_int, vp, i64, C.c_int, vp, vp, i64, vp, vp],
@@ -79,7 +88,9 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError here means header and library disagree
             fn.argtypes = argtypes
-            fn.restype = C.c_char_p if name == "b200mnn_last_error" else (C.c_int64 if name == "b200mnn_launch_count" else C.c_int)
+            fn.restype = (C.c_char_p if name == "b200mnn_last_error" else
+                          C.c_int64 if name in ("b200mnn_launch_count", "b200mnn_result_ncells", "b200mnn_result_npairs") else
+                          None if name == "b200mnn_result_free" else C.c_int)
         _lib = lib
     return _lib
 

@@ -423,12 +423,105 @@ def _finish(tree, full, pairings, left_set, right_set, extra) -> MNNResult:
     return MNNResult(corrected=full, batch=full_origin, merge_info=info)
 
 
-def _fast_mnn_core(batches, k, prop_k, restrict, ndist, merge_order, min_batch_skip, get_variance=True) -> MNNResult:
+class _Final:
+    """What :func:`_finish` needs of the final tree node."""
+
+    def __init__(self, index, origin):
+        self.index = index
+        self.origin = origin
+
+
+def _merge_sequence(nb: int, merge_order):
+    """Flattens the merge tree into the order .get_next_merge walks it (R/MNN_tree.R:61-69): node ids 0..nb-1 are the
+    batches, merge m creates node nb + m.  Returns (left ids, right ids, batches of each left node, of each right node)."""
+    tree = _predefined_tree(nb, merge_order)
+    members = {i: [i + 1] for i in range(nb)}
+
+    def to_ids(t):
+        return [to_ids(t[0]), to_ids(t[1])] if isinstance(t, list) else int(t) - 1
+
+    tree = to_ids(tree)
+    lefts, rights, lset, rset = [], [], [], []
+    for m in range(nb - 1):
+        left, right, path = _next_merge(tree)
+        lefts.append(left); rights.append(right)
+        lset.append(list(members[left])); rset.append(list(members[right]))
+        members[nb + m] = members[left] + members[right]
+        tree = _update(tree, path, nb + m)
+    return lefts, rights, lset, rset
+
+
+def _fast_mnn_core_c(batches, k, prop_k, restrict, ndist, merge_order, min_batch_skip, get_variance=True, auto_merge=False) -> MNNResult:
+    """The merge loop as ONE call of the C ABI (b200mnn_reduced_mnn, csrc/merge.cu): what the R shim does.  With
+    ``auto_merge`` the merge order is searched on the device (R/MNN_tree.R:154-226) and read back afterwards."""
+    nb = len(batches)
+    d = batches[0].shape[1]
+    mats = []
+    for b in batches:
+        if b.ndim != 2 or b.shape[1] != d:
+            raise ValueError("number of columns is not the same across batches")
+        mats.append(np.ascontiguousarray(b, dtype=np.float64))
+    if auto_merge:
+        lefts, rights, left_set, right_set = [], [], [], []
+    else:
+        lefts, rights, left_set, right_set = _merge_sequence(nb, merge_order)
+    ptrs = (_lib.f64p * nb)(*[_fp(m) for m in mats])
+    ncells = (C.c_int64 * nb)(*[m.shape[0] for m in mats])
+    ml = np.asarray(lefts, dtype=np.int32); mr = np.asarray(rights, dtype=np.int32)
+    rptr, rn, keep = None, None, []
+    if restrict is not None:
+        keep = [None if r is None else np.ascontiguousarray(r, dtype=np.int32) for r in restrict]
+        rptr = (_lib.i32p * nb)(*[C.cast(None, _lib.i32p) if r is None else _ip(r) for r in keep])
+        rn = (C.c_int64 * nb)(*[0 if r is None else r.size for r in keep])
+    skip = float("nan") if (min_batch_skip is None or (isinstance(min_batch_skip, float) and math.isnan(min_batch_skip))) else float(min_batch_skip)
+    handle = C.c_void_p(None)
+    _lib.call("b200mnn_reduced_mnn", ptrs, ncells, nb, d, 0, _ip(ml) if (nb > 1 and not auto_merge) else None,
+              _ip(mr) if (nb > 1 and not auto_merge) else None, int(k),
+              -1.0 if prop_k is None else float(prop_k), float(ndist), skip, rptr, rn, 1 if get_variance else 0, C.byref(handle))
+    try:
+        ntotal = int(_lib.load().b200mnn_result_ncells(handle))
+        corrected = np.empty((ntotal, d), dtype=np.float64)
+        _lib.call("b200mnn_result_corrected", handle, _fp(corrected), 0)
+        order = np.zeros(nb, dtype=np.int32); counts = np.zeros(nb, dtype=np.int64)
+        nm = nb - 1
+        batch_size = np.full(max(nm, 1), np.nan); skipped = np.zeros(max(nm, 1), dtype=np.int32); lost = np.zeros((max(nm, 1), nb))
+        _lib.call("b200mnn_result_info", handle, _ip(order), counts.ctypes.data_as(_lib.i64p), _fp(batch_size), _ip(skipped), _fp(lost))
+        if auto_merge and nm > 0:
+            gl = np.zeros(nm, dtype=np.int32); gr = np.zeros(nm, dtype=np.int32)
+            _lib.call("b200mnn_result_merges", handle, _ip(gl), _ip(gr))
+            members = {i: [i + 1] for i in range(nb)}
+            for m in range(nm):
+                left_set.append(list(members[int(gl[m])])); right_set.append(list(members[int(gr[m])]))
+                members[nb + m] = members[int(gl[m])] + members[int(gr[m])]
+        pairings = []
+        for m in range(nm):
+            npairs = int(_lib.load().b200mnn_result_npairs(handle, m))
+            first = np.zeros(max(npairs, 1), dtype=np.int32); second = np.zeros(max(npairs, 1), dtype=np.int32)
+            _lib.call("b200mnn_result_pairs", handle, m, _ip(first), _ip(second))
+            pairings.append((first[:npairs].astype(np.int64) - 1, second[:npairs].astype(np.int64) - 1))
+    finally:
+        _lib.load().b200mnn_result_free(handle)
+    final = _Final([int(x) for x in order], np.repeat(order.astype(np.int64), counts))
+    if nm == 0:
+        return _finish(final, corrected, [], [], [], dict(batch_size=np.zeros(0), skipped=np.zeros(0, bool), lost_var=np.zeros((0, 1))))
+    return _finish(final, corrected, pairings, left_set, right_set,
+                   dict(batch_size=batch_size[:nm], skipped=skipped[:nm].astype(bool), lost_var=lost[:nm]))
+
+
+def _fast_mnn_core(batches, k, prop_k, restrict, ndist, merge_order, min_batch_skip, get_variance=True, auto_merge=False) -> MNNResult:
+    """One call of the C ABI (device-resident merge loop, all visible GPUs driven from this process) -- unless this process
+    is one rank of a torch.distributed job (one GPU per process: the loop below shards the searches over the ranks) or
+    B200MNN_PYLOOP=1 asks for the Python-driven loop."""
+    import os
+
     import torch
 
     from . import device as dev
 
     dev.require_cuda()
+    in_group = torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+    if auto_merge or (not in_group and os.environ.get("B200MNN_PYLOOP") != "1"):
+        return _fast_mnn_core_c(batches, k, prop_k, restrict, ndist, merge_order, min_batch_skip, get_variance, auto_merge)
     cuda = torch.device("cuda", torch.cuda.current_device())
     nb = len(batches)
     d = batches[0].shape[1]
@@ -536,20 +629,18 @@ def reducedMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, ndist=3, 
     """reducedMNN (R/reducedMNN.R:61-95): MNN correction of precomputed low-dimensional coordinates [cells x dims]."""
     _check_bpparam(BPPARAM)
     _select_device(BNPARAM)
-    if auto_merge:
-        raise NotImplementedError("auto.merge=TRUE is not part of the accelerated path yet (SURVEY.md section 8f, N3)")
     mats = [np.asarray(b, dtype=np.float64) for b in batches]
     if len(mats) == 0:
         raise ValueError("at least one batch must be supplied")
     if len(mats) == 1:
         parts, reorder, restricted, _ = _divide_into_batches(mats[0], batch, True, None if restrict is None else restrict[0])
-        out = _fast_mnn_core(parts, k, prop_k, restricted, ndist, merge_order, min_batch_skip)
+        out = _fast_mnn_core(parts, k, prop_k, restricted, ndist, merge_order, min_batch_skip, auto_merge=auto_merge)
         out.corrected = out.corrected[reorder - 1]
         out.batch = out.batch[reorder - 1]
         out.merge_info["pairs"] = _reindex_pairings(out.merge_info["pairs"], reorder)
         return out
     restrict = _check_restrict([m.shape[0] for m in mats], restrict)
-    return _fast_mnn_core(mats, k, prop_k, restrict, ndist, merge_order, min_batch_skip)
+    return _fast_mnn_core(mats, k, prop_k, restrict, ndist, merge_order, min_batch_skip, auto_merge=auto_merge)
 
 
 def fastMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, cos_norm=True, ndist=3, d=50, merge_order=None,

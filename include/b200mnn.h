@@ -116,6 +116,42 @@ int b200mnn_tricube_weighted_correction(const double* curdata, int64_t n, int d,
                                         const int32_t* in_mnn, int64_t nmnn, int k, double ndist, double* out);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * The whole merge loop as one call: reducedMNN / .fast_mnn_core, R/fastMNN.R:436-562
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Opaque result of b200mnn_reduced_mnn: the final node stays in HBM until it is fetched. */
+typedef struct b200mnn_merge_result b200mnn_merge_result;
+
+/* batches[b]: host matrix of batch b, [ncells[b] x d] (col_major != 0: R layout).  The merge ORDER is host control flow
+ * (the R side walks its MNN_treenode tree, R/MNN_tree.R:61-109) and arrives flattened: leaves are nodes 0..nb-1, merge m
+ * (0-based) merges nodes merge_left[m] (reference side, "left") and merge_right[m] (corrected side) into node nb + m.
+ * merge_left == NULL: auto.merge = TRUE -- the order is searched on the device as R/MNN_tree.R:154-226 does (MNN pair
+ * counts of every pair of remaining nodes, largest first; b200mnn_result_merges reports what was chosen).
+ * k, prop_k (< 0 or NaN: NULL), ndist, min_batch_skip (NaN: never test) as in R/fastMNN.R:283-287; restrict1[b]: 1-based
+ * rows of batch b or NULL (restrict1 itself may be NULL); get_variance != 0 fills lost_var.
+ * Every visible CUDA device that can peer with the current one is used (query rows sharded, reference rows replicated
+ * over NVLink); B200MNN_DEVICES=n caps the number.  Error strings are the reference's where it has one. */
+int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int nb, int d, int col_major, const int32_t* merge_left,
+                        const int32_t* merge_right, int k, double prop_k, double ndist, double min_batch_skip,
+                        const int32_t* const* restrict1, const int64_t* nrestrict, int get_variance, b200mnn_merge_result** result_out);
+/* Total number of cells / number of MNN pairs of merge m (-1: bad argument). */
+int64_t b200mnn_result_ncells(const b200mnn_merge_result* res);
+int64_t b200mnn_result_npairs(const b200mnn_merge_result* res, int merge);
+/* Pairs of merge m: 1-based ROW NUMBERS WITHIN the left and the right node of that merge, in the order of
+ * src/find_mutual_nns.cpp:23-37 (the R side shifts them to output positions, R/fastMNN.R:533-538). */
+int b200mnn_result_pairs(const b200mnn_merge_result* res, int merge, int32_t* left_out, int32_t* right_out);
+/* Corrected coordinates [ntotal x d] in the row order of the final node (see node_order below). */
+int b200mnn_result_corrected(const b200mnn_merge_result* res, double* out, int col_major);
+/* node_order int32[nb]: batches (1-based) in the row order of the final node, node_ncells int64[nb]: their row counts;
+ * batch_size double[nb-1], skipped int32[nb-1], lost_var double[(nb-1) x nb] row-major (metadata(out)$merge.info,
+ * R/fastMNN.R:549-560).  Any pointer may be NULL. */
+int b200mnn_result_info(const b200mnn_merge_result* res, int32_t* node_order, int64_t* node_ncells, double* batch_size, int32_t* skipped,
+                        double* lost_var);
+/* Node ids (see above) merged at every step: the given order, or the one the auto-merge search chose.  int32[nb-1] each. */
+int b200mnn_result_merges(const b200mnn_merge_result* res, int32_t* left_out, int32_t* right_out);
+void b200mnn_result_free(b200mnn_merge_result* res);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Device-pointer entry points (row-major [cells x dims] double, int32 0-based ids, cudaStream_t as void*)
  * ------------------------------------------------------------------------------------------------------------ */
 

@@ -240,18 +240,44 @@ def reindex_pairings(pairings, new_order):
 # ------------------------------------------------------------------------------------------------
 # R/fastMNN.R:436-562  .fast_mnn_core  (predefined merge tree; reducedMNN = this on given PCs, R/reducedMNN.R:61-95)
 # ------------------------------------------------------------------------------------------------
+def _count_mnn_pairs(left, remainders, upto, k, prop_k, mutual):
+    """R/MNN_tree.R:171-193 .count_mnn_pairs: note that left.data keeps the centrings of every earlier iteration."""
+    ld = left.data
+    n = np.zeros(upto, dtype=np.int64)
+    for j in range(upto):
+        right = remainders[j]
+        rd = orthogonalize_other(right.data, right.restrict, left.extras)
+        ld = orthogonalize_other(ld, left.restrict, right.extras)
+        first, _ = restricted_mnn(ld, left.restrict, rd, right.restrict, k, prop_k, mutual=mutual)
+        n[j] = len(first)
+    return n
+
+
 def reduced_mnn(batches, k=20, prop_k=None, restrict=None, ndist=3, merge_order=None, min_batch_skip=0.0,
-                knn=None, mutual=None):
+                knn=None, mutual=None, auto_merge=False):
     batches = [np.asarray(b, dtype=np.float64) for b in batches]
     nb = len(batches)
-    tree = create_tree_predefined(batches, restrict, merge_order)
+    if auto_merge:   # R/MNN_tree.R:154-168 .initialize_auto_search
+        remainders = [Node([i + 1], batches[i], None if restrict is None else restrict[i]) for i in range(nb)]
+        pairwise = np.zeros((nb, nb), dtype=np.int64)
+        for i in range(nb):
+            pairwise[i, :i] = _count_mnn_pairs(remainders[i], remainders, i, k, prop_k, mutual)
+        tree = None
+    else:
+        tree = create_tree_predefined(batches, restrict, merge_order)
     nmerges = nb - 1
     pairings, left_set, right_set = [], [], []
     batch_size = np.full(nmerges, np.nan)
     skipped = np.zeros(nmerges, dtype=bool)
     var_kept = np.ones((nmerges, nb))
     for mdx in range(nmerges):
-        left, right, path = get_next_merge(tree)
+        if auto_merge:   # .pick_best_merge (:196-202): which(stats == max(stats), arr.ind=TRUE)[1,] -> column-major first
+            best = pairwise.max()
+            cols, rows = np.nonzero(pairwise.T == best)
+            chosen = (int(rows[0]), int(cols[0]))
+            left, right = remainders[chosen[0]], remainders[chosen[1]]
+        else:
+            left, right, path = get_next_merge(tree)
         ld, rd = left.data, right.data
         left_old = compute_perbatch_var(ld, left.index, left.origin)
         right_old = compute_perbatch_var(rd, right.index, right.origin)
@@ -287,7 +313,18 @@ def reduced_mnn(batches, k=20, prop_k=None, restrict=None, ndist=3, merge_order=
         node = Node(left.index + right.index, np.vstack([ld, rd]),
                     combine_restrict(ld.shape[0], left.restrict, rd.shape[0], right.restrict),
                     origin=np.concatenate([left.origin, right.origin]), extras=left.extras + right.extras + to_add)
-        tree = update_tree(tree, path, node)
+        if auto_merge:   # .update_remainders (:205-226)
+            keep = [i for i in range(len(remainders)) if i not in chosen]
+            remainders = [remainders[i] for i in keep]
+            if remainders:
+                old = pairwise[np.ix_(keep, keep)]
+                new_stats = _count_mnn_pairs(node, remainders, len(remainders), k, prop_k, mutual)
+                pairwise = np.hstack([np.vstack([old, new_stats[None, :]]), np.zeros((len(keep) + 1, 1), dtype=np.int64)])
+                remainders.append(node)
+            else:
+                tree = node
+        else:
+            tree = update_tree(tree, path, node)
     return _finish(tree, tree.data, pairings, left_set, right_set,
                    dict(batch_size=batch_size, skipped=skipped, lost_var=1 - var_kept))
 

@@ -558,3 +558,38 @@ def test_query_knn_wide_path_ties_and_gene_space():
     got = bb.findMutualNN(A.T, B.T, k1=20, k2=20)
     f, s = capi.find_mutual_nn(np.ascontiguousarray(A.T), np.ascontiguousarray(B.T), 20, 20)
     assert np.array_equal(got["first"], f) and np.array_equal(got["second"], s)
+
+
+def test_reduced_mnn_single_c_abi_call_equals_python_driven_loop(monkeypatch):
+    """b200mnn_reduced_mnn (the device-resident merge loop as one C-ABI call) against the Python-driven loop
+    over the per-step entry points and against the numpy oracle: 4 batches, hierarchical merge order, restrict, prop.k."""
+    rng = np.random.default_rng(77)
+    Bs = [rng.normal(size=(n, 12)) + 0.8 * i for i, n in enumerate([500, 420, 380, 610])]
+    restrict = [np.arange(1, 451), None, np.arange(20, 381), None]
+    kw = dict(k=15, merge_order=[[1, 2], [4, 3]], restrict=restrict, prop_k=0.05)
+    one = bb.reducedMNN(*Bs, **kw)
+    monkeypatch.setenv("B200MNN_PYLOOP", "1")
+    two = bb.reducedMNN(*Bs, **kw)
+    assert np.array_equal(one.batch, two.batch)
+    assert _relerr(one.corrected, two.corrected) < 1e-12
+    for a, b in zip(one.merge_info["pairs"], two.merge_info["pairs"]):
+        assert np.array_equal(a["left"], b["left"]) and np.array_equal(a["right"], b["right"])
+    assert np.allclose(one.merge_info["lost_var"], two.merge_info["lost_var"], rtol=1e-9, atol=1e-12)
+    assert one.merge_info["left"] == two.merge_info["left"] and one.merge_info["right"] == two.merge_info["right"]
+    ref = ho.reduced_mnn(Bs, **kw)
+    assert _relerr(one.corrected, ref["corrected"]) < RTOL
+    assert np.allclose(one.merge_info["lost_var"], ref["merge_info"]["lost_var"], rtol=1e-5, atol=1e-8)
+
+
+def test_reduced_mnn_auto_merge_matches_oracle():
+    """auto.merge = TRUE (R/MNN_tree.R:154-226) searched on the device inside b200mnn_reduced_mnn: same merge order, same
+    pairs, same corrected values as the numpy restatement; 4 batches so that a merged node is re-counted with orthogonalisation."""
+    rng = np.random.default_rng(9)
+    A = rng.normal(size=(400, 8)); B = rng.normal(size=(350, 8)) + 0.4; Cc = rng.normal(size=(300, 8)); Cc[:, 0] += 5.0
+    D = rng.normal(size=(320, 8)); D[:, 0] += 5.3
+    got = bb.reducedMNN(A, Cc, B, D, k=12, auto_merge=True)
+    ref = ho.reduced_mnn([A, Cc, B, D], k=12, auto_merge=True)
+    assert got.merge_info["left"] == ref["merge_info"]["left"] and got.merge_info["right"] == ref["merge_info"]["right"]
+    for a, b in zip(got.merge_info["pairs"], ref["merge_info"]["pairs"]):
+        assert np.array_equal(a["left"], b[0]) and np.array_equal(a["right"], b[1])
+    assert np.array_equal(got.batch, ref["batch"]) and _relerr(got.corrected, ref["corrected"]) < RTOL

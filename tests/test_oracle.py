@@ -288,3 +288,16 @@ def test_lost_var_is_recorded_before_the_tricube_step():
     v = averaged.mean(axis=0); v /= np.linalg.norm(v)
     want = [np.var(X @ v, ddof=1) / np.var(X, axis=0, ddof=1).sum() for X in (b1, b2)]
     assert np.allclose(res["merge_info"]["lost_var"][0], want, rtol=1e-9, atol=1e-12)
+
+
+def test_auto_merge_picks_the_pair_with_most_mnn_pairs():
+    """R/MNN_tree.R:154-226: with two overlapping batches and one distant batch the first merge must be the overlapping
+    pair, and the result must equal the predefined order that auto.merge discovers."""
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(200, 6)); B = rng.normal(size=(180, 6)) + 0.3; Cc = rng.normal(size=(150, 6)); Cc[:, 0] += 6.0
+    auto = ho.reduced_mnn([A, Cc, B], k=10, auto_merge=True)
+    first = (auto["merge_info"]["left"][0], auto["merge_info"]["right"][0])
+    assert sorted(first[0] + first[1]) == [1, 3]
+    lhs, rhs = first[0][0], first[1][0]
+    fixed = ho.reduced_mnn([A, Cc, B], k=10, merge_order=[lhs, rhs, 2])
+    assert np.allclose(auto["corrected"], fixed["corrected"], rtol=0, atol=0)
