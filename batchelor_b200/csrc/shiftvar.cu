@@ -23,7 +23,9 @@
 //                       EXACT: two sweeps over the genes (projection + scale, then the distance), 10 fp64 ops per gene
 //                              and pair, bit-identical to the reference;
 //                       FAST : one sweep of two FMAs per gene and pair (projection and Gram entry; Appendix A7 of
-//                              SURVEY.md), error ~1e-13, for the bulk; every decision it feeds is certified below.
+//                              SURVEY.md), error ~1e-13, for the bulk; every decision it feeds is certified below.  The
+//                              default FAST kernel (sv_pairs_dmma_kernel) runs the two contractions on the fp64 tensor
+//                              cores (mma.sync.m8n8k4.f64); B200MNN_SHIFTVAR=fast_simt keeps them on the CUDA cores.
 //                     Own batch: running (masked, total) log-sum-exp per cell.  Reference batch: (projection,
 //                     log-weight) rows written to a chunk buffer + running total, min and max projection.
 //   sv_select_kernel  one CTA per cell: weighted-quantile SELECTION instead of a sort -- histogram of the weights over
@@ -334,6 +336,175 @@ sv_pairs_kernel(const double* __restrict__ grad, const double* __restrict__ data
             o[0] = l_a[a].m; o[1] = l_a[a].s;
             o[2] = OWN ? l_b[a].m : pmin[a];
             o[3] = OWN ? l_b[a].s : pmax[a];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pairs, FAST mode on the fp64 tensor cores (DMMA m8n8k4)
+// ------------------------------------------------------------------------------------------------
+// Same tile (64 cells x 64 comparison cells, genes staged in chunks of 16) and same epilogue as sv_pairs_kernel<false>;
+// the two contractions (projection g_c . x and Gram entry x_c . x) run as mma.sync.m8n8k4.f64: 8 warps = 4 row groups
+// (16 cells: two m8 blocks of the g rows and two of the x_c rows) x 2 column groups (32 cells: four n8 blocks), 16 DMMAs
+// per 4 genes fed by 8 conflict-free LDS.64 -- the SIMT form needs 12 LDS.64 per 32 FMAs and is shared-memory bound.
+// Partial results are written per (row, split, column group): the partial arrays hold 2 * nsplit entries per row.
+constexpr int DM_KP = 20;   // shared-memory row pitch in doubles (rows of 16 staged genes): half-warps hit 16 distinct banks
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <bool OWN>
+__global__ void __launch_bounds__(THREADS)
+sv_pairs_dmma_kernel(const double* __restrict__ grad, const double* __restrict__ data2, const double* __restrict__ curproj,
+                     const double* __restrict__ norm2, int64_t c0, int64_t nrows, const double* __restrict__ other,
+                     const double* __restrict__ onorm, const int32_t* __restrict__ ridx, int64_t ncols, int64_t G, double sigma2, double amb,
+                     double* __restrict__ Pout, double* __restrict__ Wout, int64_t ld, double* __restrict__ part, int nsplit, int tiles_per_split) {
+    __shared__ __align__(16) double Gs[TS][DM_KP];
+    __shared__ __align__(16) double Cs[TS][DM_KP];
+    __shared__ __align__(16) double Xs[TS][DM_KP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rg = warp & 3, cg = warp >> 2;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;   // loader: row lr of the tile, 4 consecutive genes
+    const int64_t rb = (int64_t)blockIdx.y * TS;
+    const int split = blockIdx.x;
+    const int64_t ncoltiles = (ncols + TS - 1) / TS;
+    const int64_t t_begin = (int64_t)split * tiles_per_split, t_end = min(ncoltiles, t_begin + tiles_per_split);
+    const int64_t arow = (rb + lr < nrows) ? c0 + rb + lr : -1;
+
+    // this lane's two rows (m block 0 / 1)
+    double cp[2], cn[2];
+    int64_t cell[2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        const int64_t r = rb + rg * 16 + mb * 8 + gid;
+        cell[mb] = (r < nrows) ? c0 + r : -1;
+        cp[mb] = (r < nrows) ? curproj[c0 + r] : 0.0;
+        cn[mb] = (r < nrows) ? norm2[c0 + r] : 0.0;
+    }
+    LSE l_a[2], l_b[2];
+    double pmin[2], pmax[2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) { l_a[mb] = {-INFINITY, 0.0}; l_b[mb] = {-INFINITY, 0.0}; pmin[mb] = INFINITY; pmax[mb] = -INFINITY; }
+
+    for (int64_t ct = t_begin; ct < t_end; ++ct) {
+        const int64_t cb = ct * TS;
+        const int64_t brow = (cb + lr < ncols) ? (int64_t)ridx[cb + lr] : -1;
+        double accP[2][4][2], accD[2][4][2];
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) { accP[mb][nb][0] = accP[mb][nb][1] = 0.0; accD[mb][nb][0] = accD[mb][nb][1] = 0.0; }
+        double pg[4], pc[4], px[4];
+        auto fetch = [&](int64_t k0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = k0 + lk + j;
+                const bool kin = k < G;
+                pg[j] = (arow >= 0 && kin) ? grad[arow * G + k] : 0.0;
+                pc[j] = (arow >= 0 && kin) ? data2[arow * G + k] : 0.0;
+                px[j] = (brow >= 0 && kin) ? other[brow * G + k] : 0.0;
+            }
+        };
+        fetch(0);
+        for (int64_t k0 = 0; k0 < G; k0 += KC) {
+            __syncthreads();
+            *reinterpret_cast<double2*>(&Gs[lr][lk]) = make_double2(pg[0], pg[1]);
+            *reinterpret_cast<double2*>(&Gs[lr][lk + 2]) = make_double2(pg[2], pg[3]);
+            *reinterpret_cast<double2*>(&Cs[lr][lk]) = make_double2(pc[0], pc[1]);
+            *reinterpret_cast<double2*>(&Cs[lr][lk + 2]) = make_double2(pc[2], pc[3]);
+            *reinterpret_cast<double2*>(&Xs[lr][lk]) = make_double2(px[0], px[1]);
+            *reinterpret_cast<double2*>(&Xs[lr][lk + 2]) = make_double2(px[2], px[3]);
+            __syncthreads();
+            if (k0 + KC < G) fetch(k0 + KC);
+#pragma unroll
+            for (int k4 = 0; k4 < KC / 4; ++k4) {
+                double ag[2], ac[2], bx[4];
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    ag[mb] = Gs[rg * 16 + mb * 8 + gid][k4 * 4 + tig];
+                    ac[mb] = Cs[rg * 16 + mb * 8 + gid][k4 * 4 + tig];
+                }
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) bx[nb] = Xs[cg * 32 + nb * 8 + gid][k4 * 4 + tig];
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        dmma(accP[mb][nb][0], accP[mb][nb][1], ag[mb], bx[nb]);
+                        dmma(accD[mb][nb][0], accD[mb][nb][1], ac[mb], bx[nb]);
+                    }
+            }
+        }
+        // ---- tile epilogue (same arithmetic as the SIMT form) ----
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int64_t j = cb + cg * 32 + nb * 8 + tig * 2 + i;
+                if (j >= ncols) continue;
+                const int64_t oidx = ridx[j];
+                const double xn = onorm[oidx];
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    if (cell[mb] < 0) continue;
+                    const double pr = accP[mb][nb][i];
+                    const double dp = cp[mb] - pr;
+                    double d2 = (cn[mb] + xn) - 2.0 * accD[mb][nb][i] - dp * dp;
+                    d2 = fmax(d2, 0.0);
+                    double lwv = -d2 / sigma2;
+                    if (OWN) {
+                        bool add = true;
+                        double logp = 0.0;
+                        if (oidx != cell[mb]) {
+                            logp = lwv;
+                            double sp = pr;
+                            if (fabs(sp - cp[mb]) <= amb) {   // undecidable in FMA order: redo this pair in the reference's order
+                                double ep, ed;
+                                exact_pair(grad + cell[mb] * G, data2 + cell[mb] * G, other + oidx * G, G, ep, ed);
+                                sp = ep;
+                                logp = __ddiv_rn(-ed, sigma2);
+                            }
+                            if (sp > cp[mb]) add = false;
+                        }
+                        if (add) lse_add(l_a[mb], logp);
+                        lse_add(l_b[mb], logp);
+                    } else {
+                        const int64_t o = (rb + rg * 16 + mb * 8 + gid) * ld + j;
+                        Pout[o] = pr;
+                        Wout[o] = lwv;
+                        lse_add(l_a[mb], lwv);
+                        pmin[mb] = fmin(pmin[mb], pr);
+                        pmax[mb] = fmax(pmax[mb], pr);
+                    }
+                }
+            }
+    }
+    // the four lanes of a group (tig) share the lane's two rows
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            LSE oa, ob;
+            oa.m = __shfl_xor_sync(0xffffffffu, l_a[mb].m, o);
+            oa.s = __shfl_xor_sync(0xffffffffu, l_a[mb].s, o);
+            lse_merge(l_a[mb], oa);
+            if (OWN) {
+                ob.m = __shfl_xor_sync(0xffffffffu, l_b[mb].m, o);
+                ob.s = __shfl_xor_sync(0xffffffffu, l_b[mb].s, o);
+                lse_merge(l_b[mb], ob);
+            } else {
+                pmin[mb] = fmin(pmin[mb], __shfl_xor_sync(0xffffffffu, pmin[mb], o));
+                pmax[mb] = fmax(pmax[mb], __shfl_xor_sync(0xffffffffu, pmax[mb], o));
+            }
+        }
+        const int64_t r = rb + rg * 16 + mb * 8 + gid;
+        if (tig == 0 && r < nrows) {
+            double* o = part + (r * (2 * nsplit) + 2 * split + cg) * 4;
+            o[0] = l_a[mb].m; o[1] = l_a[mb].s;
+            o[2] = OWN ? l_b[mb].m : pmin[mb];
+            o[3] = OWN ? l_b[mb].s : pmax[mb];
         }
     }
 }
@@ -734,11 +905,12 @@ row_norm2_kernel(const double* __restrict__ X, int64_t n, int64_t G, double* __r
     }
 }
 
-static int mode_from_env() {   // 0 = exact tiles, 1 = fast tiles (default), 2 = per-cell loop
+static int mode_from_env() {   // 0 = exact tiles, 1 = fast tiles on the fp64 tensor cores (default), 2 = per-cell loop, 3 = fast tiles, SIMT
     const char* e = getenv("B200MNN_SHIFTVAR");
     if (!e) return 1;
     if (strcmp(e, "exact") == 0) return 0;
     if (strcmp(e, "cell") == 0) return 2;
+    if (strcmp(e, "fast_simt") == 0) return 3;
     return 1;
 }
 
@@ -833,8 +1005,10 @@ int adjust_shift_variance_device(const double* d_data1, int64_t n1, const double
     const int tps1 = (int)ceil_div(ct1, ns1), tps2 = (int)ceil_div(ct2, ns2);
     double* Pbuf = ws.get<double>((size_t)std::min(chunk, round_up(n2, TS)) * ld);
     double* Wbuf = ws.get<double>((size_t)std::min(chunk, round_up(n2, TS)) * ld);
-    double* part1 = ws.get<double>((size_t)chunk * ns1 * 4);
-    double* part2 = ws.get<double>((size_t)chunk * ns2 * 4);
+    const bool use_dmma = (mode == 1);
+    const int pm = use_dmma ? 2 : 1;   // the DMMA kernel writes one partial per (split, column group)
+    double* part1 = ws.get<double>((size_t)chunk * ns1 * pm * 4);
+    double* part2 = ws.get<double>((size_t)chunk * ns2 * pm * 4);
     if (!ws.ok()) return B200MNN_ENOMEM;
     for (int64_t c0 = 0; c0 < n2; c0 += chunk) {
         const int64_t nrows = std::min(chunk, n2 - c0);
@@ -844,6 +1018,9 @@ int adjust_shift_variance_device(const double* d_data1, int64_t n1, const double
             if (exact)
                 sv_pairs_kernel<true, true><<<grid, THREADS, 0, stream>>>(grad, d_data2, curproj, norm_2, c0, nrows, d_data2, norm_2, d_r2, nr2, G, sigma2,
                                                                           amb, nullptr, nullptr, 0, part2, ns2, tps2);
+            else if (use_dmma)
+                sv_pairs_dmma_kernel<true><<<grid, THREADS, 0, stream>>>(grad, d_data2, curproj, norm_2, c0, nrows, d_data2, norm_2, d_r2, nr2, G, sigma2,
+                                                                         amb, nullptr, nullptr, 0, part2, ns2, tps2);
             else
                 sv_pairs_kernel<false, true><<<grid, THREADS, 0, stream>>>(grad, d_data2, curproj, norm_2, c0, nrows, d_data2, norm_2, d_r2, nr2, G, sigma2,
                                                                            amb, nullptr, nullptr, 0, part2, ns2, tps2);
@@ -854,13 +1031,16 @@ int adjust_shift_variance_device(const double* d_data1, int64_t n1, const double
             if (exact)
                 sv_pairs_kernel<true, false><<<grid, THREADS, 0, stream>>>(grad, d_data2, curproj, norm_2, c0, nrows, d_data1, norm_1, d_r1, nr1, G, sigma2,
                                                                            amb, Pbuf, Wbuf, ld, part1, ns1, tps1);
+            else if (use_dmma)
+                sv_pairs_dmma_kernel<false><<<grid, THREADS, 0, stream>>>(grad, d_data2, curproj, norm_2, c0, nrows, d_data1, norm_1, d_r1, nr1, G, sigma2,
+                                                                          amb, Pbuf, Wbuf, ld, part1, ns1, tps1);
             else
                 sv_pairs_kernel<false, false><<<grid, THREADS, 0, stream>>>(grad, d_data2, curproj, norm_2, c0, nrows, d_data1, norm_1, d_r1, nr1, G, sigma2,
                                                                             amb, Pbuf, Wbuf, ld, part1, ns1, tps1);
             B200_LAUNCH_CHECK();
         }
         const int sgrid = (int)std::min<int64_t>(nrows, (int64_t)sm_count() * 8);
-        sv_select_kernel<<<sgrid, THREADS, 0, stream>>>(Pbuf, Wbuf, ld, nr1, part2, ns2, nr2, part1, ns1, c0, nrows, grad, d_data1, d_r1, G, curproj, l2,
+        sv_select_kernel<<<sgrid, THREADS, 0, stream>>>(Pbuf, Wbuf, ld, nr1, part2, ns2 * pm, nr2, part1, ns1 * pm, c0, nrows, grad, d_data1, d_r1, G, curproj, l2,
                                                         tol, exact ? 0.0 : amb, d_out, flag_count, flag_list);
         B200_LAUNCH_CHECK();
     }

@@ -321,7 +321,7 @@ def test_smooth_gaussian_kernel_more_genes_out_than_in_and_errors():
         bb.smooth_gaussian_kernel(avg, idx + 700, mat, 0.1)
 
 
-@pytest.mark.parametrize("mode", ["fast", "exact", "cell"])
+@pytest.mark.parametrize("mode", ["fast", "fast_simt", "exact", "cell"])
 def test_adjust_shift_variance_matches_golden(golden, mode, monkeypatch):
     """Bit-equal to the reference object code (tests/golden/make_golden.py) in every mode: FMA-order bulk + certificate
     (default), reference-order tiles, and the reference's loop per cell.  Identical doubles == identical quantile picks."""
@@ -335,7 +335,7 @@ def test_adjust_shift_variance_matches_golden(golden, mode, monkeypatch):
     assert np.array_equal(out, g["out_restricted"])
 
 
-@pytest.mark.parametrize("mode", ["fast", "exact"])
+@pytest.mark.parametrize("mode", ["fast", "fast_simt", "exact"])
 @pytest.mark.parametrize("n1,n2,G,sigma", [(3000, 700, 37, 0.5), (5000, 300, 130, 1.0), (700, 300, 2100, 0.1)])
 def test_adjust_shift_variance_matches_oracle_bit_exact(n1, n2, G, sigma, mode, monkeypatch):
     """Larger shapes than the goldens: several column splits, bins of > 1 024 cells (second selection level), ragged

@@ -14,7 +14,7 @@ g = torch.Generator(device="cuda").manual_seed(1)
 vect = torch.randn((n2, G), dtype=torch.float64, device=cuda, generator=g) * 0.01
 r1 = torch.arange(n1, device=cuda, dtype=torch.int32); r2 = torch.arange(n2, device=cuda, dtype=torch.int32)
 res = {}
-for mode in ("fast", "exact"):
+for mode in ("fast", "fast_simt", "exact"):
     os.environ["B200MNN_SHIFTVAR"] = mode
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -23,4 +23,4 @@ for mode in ("fast", "exact"):
     res[mode] = out
     pairs = n2 * (n1 + n2)
     print(f"{mode}: {dt:.3f} s  ({pairs * G * (10 if mode == 'exact' else 2) / dt / 1e12:.2f} T fp64 op/s, {pairs / dt / 1e9:.2f} G pairs/s)")
-print("modes identical:", bool(torch.equal(res["fast"], res["exact"])), " differing cells:", int((res["fast"] != res["exact"]).sum()))
+print("modes identical:", bool(torch.equal(res["fast"], res["exact"]) and torch.equal(res["fast_simt"], res["exact"])), " differing cells:", int((res["fast"] != res["exact"]).sum()))
