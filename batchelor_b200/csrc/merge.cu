@@ -19,8 +19,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <deque>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "gemm_tc.cuh"
@@ -50,10 +53,12 @@ __global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int32_t off) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (int32_t)i + off;
 }
-// out[t] += sum over a slab of rows of f(X[r, t]) / rows, f = identity (SQ = 0), square (SQ = 1) or squared deviation from mean[t] (SQ = 2)
+// Column moments in a FIXED summation order (no floating-point atomics: results are bit-identical run to run and for any
+// number of devices): partial[slab][t] = sum over a slab of 1 024 rows of f(X[r, t]), f = identity (SQ = 0), square
+// (SQ = 1) or squared deviation from mean[t] (SQ = 2); then out[t] = inv * sum over the slabs in slab order.
 template <int SQ>
 __global__ void __launch_bounds__(256)
-col_moment_kernel(const double* __restrict__ X, int64_t rows, int d, const double* __restrict__ mean, double inv, double* __restrict__ out) {
+col_moment_kernel(const double* __restrict__ X, int64_t rows, int d, const double* __restrict__ mean, double* __restrict__ partial) {
     const int t = blockIdx.x * 256 + threadIdx.x;
     if (t >= d) return;
     const int64_t r0 = (int64_t)blockIdx.y * 1024, r1 = min(rows, r0 + 1024);
@@ -64,7 +69,14 @@ col_moment_kernel(const double* __restrict__ X, int64_t rows, int d, const doubl
         else if (SQ == 1) s += v * v;
         else { const double dv = v - mean[t]; s += dv * dv; }
     }
-    atomicAdd(&out[t], s * inv);
+    partial[(int64_t)blockIdx.y * d + t] = s;
+}
+__global__ void col_moment_final_kernel(const double* __restrict__ partial, int64_t nslabs, int d, double inv, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d) return;
+    double s = 0.0;
+    for (int64_t b = 0; b < nslabs; ++b) s += partial[b * d + t];
+    out[t] = s * inv;
 }
 __global__ void sum_vec_kernel(const double* __restrict__ v, int d, double* __restrict__ out) {
     double s = 0.0;
@@ -109,7 +121,9 @@ struct DevBuf {   // stream-ordered device allocation, freed explicitly or at de
 };
 
 struct Node {
-    DevBuf data;                   // [n x d] row-major
+    DevBuf data;                   // [n x d] row-major, when the node owns its rows ...
+    double* ptr = nullptr;         // ... or a window of the arena (rows()) -- children of a merge are adjacent there
+    double* rows() const { return ptr ? ptr : data.as<double>(); }
     int64_t n = 0;
     DevBuf restrict_rows;          // int32 0-based rows, or empty
     int64_t nres = -1;             // -1: no restriction
@@ -125,6 +139,7 @@ struct MergeResult {
     int device0 = 0;
     cudaStream_t stream = nullptr;
     std::deque<Node> nodes;                        // 2 nb - 1 (deque: nodes are neither copied nor moved)
+    DevBuf arena;                                  // [ntotal x d]: leaves in the left-to-right leaf order of the merge tree
     std::vector<DevBuf*> vec_pool;
     std::vector<std::vector<int32_t>> pl, pr;      // pairs per merge, 1-based rows within the left / right node
     std::vector<double> batch_size, lost_var;
@@ -134,8 +149,9 @@ struct MergeResult {
     ~MergeResult() {
         if (stream) { cudaSetDevice(device0); cudaStreamSynchronize(stream); }
         nodes.clear();
+        arena.release();
         for (auto* v : vec_pool) delete v;
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     }
 };
 
@@ -185,46 +201,75 @@ struct DeviceSet {
 };
 
 // X [n x d], Q [nq x d] on the primary device (ready on `stream`); results on the primary device, ready on `stream`.
+// A helper device is worth its fixed cost (replica of X over NVLink, its own cluster plan, ~150 launches) only for a large
+// block of queries: the search uses min(G, nq / 131072) devices (B200MNN_SHARD_MIN overrides the block size), each
+// helper driven by its own host thread so that the launch streams of the devices fill concurrently.
 static int sharded_query_knn(DeviceSet& ds, const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
                              cudaStream_t stream) {
-    const int G = (int)ds.devs.size();
-    if (G == 1 || nq < (int64_t)G * 4096) return knn::query_knn_device(dX, n, dQ, nq, d, k, d_idx, d_dist, nullptr, stream, nullptr);
+    int64_t block = 131072;
+    if (const char* e = getenv("B200MNN_SHARD_MIN")) block = std::max<int64_t>(1024, atoll(e));
+    const int G = (int)std::min<int64_t>((int64_t)ds.devs.size(), std::max<int64_t>(1, nq / block));
+    if (G <= 1) return knn::query_knn_device(dX, n, dQ, nq, d, k, d_idx, d_dist, nullptr, stream, nullptr);
     const int primary = ds.devs[0];
     cudaEvent_t ready;
     B200_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     B200_CUDA(cudaEventRecord(ready, stream));
     const int64_t per = ceil_div(nq, G);
     std::vector<cudaEvent_t> done(G, nullptr);
-    int rc = 0;
-    for (int g = 1; g < G && !rc; ++g) {
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> workers;
+    for (int g = 1; g < G; ++g) {
         const int64_t lo = std::min(nq, g * per), hi = std::min(nq, (g + 1) * per);
         if (hi <= lo) continue;
-        cudaSetDevice(ds.devs[g]);
-        cudaStream_t s = ds.streams[g];
-        cudaStreamWaitEvent(s, ready, 0);
-        double *x = nullptr, *q = nullptr, *dd = nullptr;
-        int32_t* ii = nullptr;
-        cudaMallocAsync(&x, sizeof(double) * n * d, s);
-        cudaMallocAsync(&q, sizeof(double) * (hi - lo) * d, s);
-        cudaMallocAsync(&ii, sizeof(int32_t) * (hi - lo) * k, s);
-        if (d_dist) cudaMallocAsync(&dd, sizeof(double) * (hi - lo) * k, s);
-        cudaMemcpyPeerAsync(x, ds.devs[g], dX, primary, sizeof(double) * n * d, s);
-        cudaMemcpyPeerAsync(q, ds.devs[g], dQ + lo * d, primary, sizeof(double) * (hi - lo) * d, s);
-        rc = knn::query_knn_device(x, n, q, hi - lo, d, k, ii, dd, nullptr, s, nullptr);
-        cudaMemcpyPeerAsync(d_idx + lo * k, primary, ii, ds.devs[g], sizeof(int32_t) * (hi - lo) * k, s);
-        if (d_dist) cudaMemcpyPeerAsync(d_dist + lo * k, primary, dd, ds.devs[g], sizeof(double) * (hi - lo) * k, s);
-        cudaFreeAsync(x, s); cudaFreeAsync(q, s); cudaFreeAsync(ii, s);
-        if (dd) cudaFreeAsync(dd, s);
-        cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming);
-        cudaEventRecord(done[g], s);
+        workers.emplace_back([&, g, lo, hi]() {
+            const int dev = ds.devs[g];
+            cudaStream_t s = ds.streams[g];
+            auto body = [&]() -> int {
+                B200_CUDA(cudaSetDevice(dev));
+                B200_CUDA(cudaStreamWaitEvent(s, ready, 0));
+                double *x = nullptr, *q = nullptr, *dd = nullptr;
+                int32_t* ii = nullptr;
+                B200_CUDA(cudaMallocAsync(&x, sizeof(double) * n * d, s));
+                B200_CUDA(cudaMallocAsync(&q, sizeof(double) * (hi - lo) * d, s));
+                B200_CUDA(cudaMallocAsync(&ii, sizeof(int32_t) * (hi - lo) * k, s));
+                if (d_dist) B200_CUDA(cudaMallocAsync(&dd, sizeof(double) * (hi - lo) * k, s));
+                B200_CUDA(cudaMemcpyPeerAsync(x, dev, dX, primary, sizeof(double) * n * d, s));
+                B200_CUDA(cudaMemcpyPeerAsync(q, dev, dQ + lo * d, primary, sizeof(double) * (hi - lo) * d, s));
+                B200_TRY(knn::query_knn_device(x, n, q, hi - lo, d, k, ii, dd, nullptr, s, nullptr));
+                B200_CUDA(cudaMemcpyPeerAsync(d_idx + lo * k, primary, ii, dev, sizeof(int32_t) * (hi - lo) * k, s));
+                if (d_dist) B200_CUDA(cudaMemcpyPeerAsync(d_dist + lo * k, primary, dd, dev, sizeof(double) * (hi - lo) * k, s));
+                cudaFreeAsync(x, s); cudaFreeAsync(q, s); cudaFreeAsync(ii, s);
+                if (dd) cudaFreeAsync(dd, s);
+                B200_CUDA(cudaEventCreateWithFlags(&done[g], cudaEventDisableTiming));
+                B200_CUDA(cudaEventRecord(done[g], s));
+                return 0;
+            };
+            rcs[g] = body();
+            if (rcs[g]) errs[g] = b200mnn_last_error();   // the message is thread-local: carry it to the caller's thread
+        });
     }
+    int rc = knn::query_knn_device(dX, n, dQ, std::min(nq, per), d, k, d_idx, d_dist, nullptr, stream, nullptr);
+    for (auto& w : workers) w.join();
     cudaSetDevice(primary);
-    if (!rc) rc = knn::query_knn_device(dX, n, dQ, std::min(nq, per), d, k, d_idx, d_dist, nullptr, stream, nullptr);
-    for (int g = 1; g < G; ++g)
+    for (int g = 1; g < G; ++g) {
         if (done[g]) { cudaStreamWaitEvent(stream, done[g], 0); cudaEventDestroy(done[g]); }
+        if (!rc && rcs[g]) rc = fail(rcs[g], errs[g]);
+    }
     cudaEventDestroy(ready);
-    if (rc) return rc;
-    B200_CUDA(cudaGetLastError());
+    return rc;
+}
+
+template <int SQ>
+static int col_moment(const double* X, int64_t rows, int d, const double* mean, double inv, double* out, cudaStream_t s) {
+    const int64_t nslabs = ceil_div(rows, 1024);
+    DevBuf partial;
+    B200_TRY(partial.alloc(sizeof(double) * nslabs * d, s));
+    dim3 grid((unsigned)ceil_div(d, 256), (unsigned)nslabs);
+    col_moment_kernel<SQ><<<grid, 256, 0, s>>>(X, rows, d, mean, partial.as<double>());
+    B200_LAUNCH_CHECK();
+    col_moment_final_kernel<<<(unsigned)ceil_div(d, 128), 128, 0, s>>>(partial.as<double>(), nslabs, d, inv, out);
+    B200_LAUNCH_CHECK();
     return 0;
 }
 
@@ -234,12 +279,8 @@ static int total_var(const double* X, int64_t rows, int d, double* scratch /* [2
     double* mean = scratch;
     double* var = scratch + d;
     double* tot = scratch + 2 * d;
-    B200_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (2 * d + 1), s));
-    dim3 grid((unsigned)ceil_div(d, 256), (unsigned)ceil_div(rows, 1024));
-    col_moment_kernel<0><<<grid, 256, 0, s>>>(X, rows, d, nullptr, 1.0 / (double)rows, mean);
-    B200_LAUNCH_CHECK();
-    col_moment_kernel<2><<<grid, 256, 0, s>>>(X, rows, d, mean, 1.0 / (double)(rows - 1), var);
-    B200_LAUNCH_CHECK();
+    B200_TRY(col_moment<0>(X, rows, d, nullptr, 1.0 / (double)rows, mean, s));
+    B200_TRY(col_moment<2>(X, rows, d, mean, 1.0 / (double)(rows - 1), var, s));
     sum_vec_kernel<<<1, 1, 0, s>>>(var, d, tot);
     B200_LAUNCH_CHECK();
     B200_CUDA(cudaMemcpyAsync(host_out, tot, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -250,7 +291,7 @@ static int perbatch_var(const Node& nd, int d, double* scratch, std::vector<doub
     out.assign(nd.index.size(), 0.0);
     int64_t r0 = 0;
     for (size_t i = 0; i < nd.index.size(); ++i) {
-        B200_TRY(total_var(nd.data.as<double>() + r0 * d, nd.seg[i], d, scratch, &out[i], s));
+        B200_TRY(total_var(nd.rows() + r0 * d, nd.seg[i], d, scratch, &out[i], s));
         B200_CUDA(cudaStreamSynchronize(s));   // `out[i]` is pageable host memory
         r0 += nd.seg[i];
     }
@@ -300,19 +341,42 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
     B200_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), s));
     B200_TRY(scratch.alloc(sizeof(double) * (4 * (size_t)d + 8), s));
 
+    // With a given merge order every merge joins two nodes that are neighbours in the left-to-right leaf order of the
+    // tree, so the leaves are uploaded into ONE arena in that order and rbind(left, right) (:520-525) costs nothing.
+    const bool given_order = (merge_left != nullptr && merge_right != nullptr);
+    std::vector<int64_t> leaf_offset(nb, -1);
+    for (int b = 0; b < nb; ++b) R.ntotal += ncells[b];
+    if (given_order && nm > 0) {
+        std::vector<std::vector<int>> leaves((size_t)2 * nb - 1);
+        for (int b = 0; b < nb; ++b) leaves[b] = {b};
+        bool ok = true;
+        for (int m = 0; m < nm && ok; ++m) {
+            const int li = merge_left[m], ri = merge_right[m];
+            ok = li >= 0 && ri >= 0 && li < nb + m && ri < nb + m && li != ri && !leaves[li].empty() && !leaves[ri].empty();
+            if (!ok) break;
+            leaves[nb + m] = leaves[li];
+            leaves[nb + m].insert(leaves[nb + m].end(), leaves[ri].begin(), leaves[ri].end());
+            leaves[li].clear(); leaves[ri].clear();
+        }
+        if (ok && (int)leaves[(size_t)2 * nb - 2].size() == nb) {
+            int64_t off = 0;
+            for (int b : leaves[(size_t)2 * nb - 2]) { leaf_offset[b] = off; off += ncells[b]; }
+            B200_TRY(R.arena.alloc(sizeof(double) * R.ntotal * d, s));
+        }
+    }
     // leaves: upload (transposing R's column-major [cells x d] on device)
     for (int b = 0; b < nb; ++b) {
         Node& nd = R.nodes[b];
         nd.n = ncells[b];
-        R.ntotal += nd.n;
-        B200_TRY(nd.data.alloc(sizeof(double) * nd.n * d, s));
+        if (R.arena.p && leaf_offset[b] >= 0) nd.ptr = R.arena.as<double>() + leaf_offset[b] * d;
+        else B200_TRY(nd.data.alloc(sizeof(double) * nd.n * d, s));
         if (col_major) {
             DevBuf raw;
             B200_TRY(raw.alloc(sizeof(double) * nd.n * d, s));
             B200_CUDA(cudaMemcpyAsync(raw.p, batches[b], sizeof(double) * nd.n * d, cudaMemcpyHostToDevice, s));
-            B200_TRY(correct::transpose_device<double>(raw.as<double>(), nd.n, d, nd.data.as<double>(), s));   // column-major [n x d] -> row-major
+            B200_TRY(correct::transpose_device<double>(raw.as<double>(), nd.n, d, nd.rows(), s));   // column-major [n x d] -> row-major
         } else {
-            B200_CUDA(cudaMemcpyAsync(nd.data.p, batches[b], sizeof(double) * nd.n * d, cudaMemcpyHostToDevice, s));
+            B200_CUDA(cudaMemcpyAsync(nd.rows(), batches[b], sizeof(double) * nd.n * d, cudaMemcpyHostToDevice, s));
         }
         if (restrict1 && restrict1[b]) {
             const int64_t nr = nrestrict[b];
@@ -383,14 +447,14 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
         counts.assign(rights.size(), 0);
         DevBuf lcopy;
         bool lcopied = false;
-        const double* ldata = left.data.as<double>();
+        const double* ldata = left.rows();
         for (size_t j = 0; j < rights.size(); ++j) {
             const Node& right = R.nodes[rights[j]];
-            const double* rdata = right.data.as<double>();
+            const double* rdata = right.rows();
             DevBuf rcopy;
             if (!left.extras.empty()) {
                 B200_TRY(rcopy.alloc(sizeof(double) * right.n * d, s));
-                B200_CUDA(cudaMemcpyAsync(rcopy.p, right.data.p, sizeof(double) * right.n * d, cudaMemcpyDeviceToDevice, s));
+                B200_CUDA(cudaMemcpyAsync(rcopy.p, right.rows(), sizeof(double) * right.n * d, cudaMemcpyDeviceToDevice, s));
                 for (DevBuf* v : left.extras)
                     B200_TRY(correct::center_along_batch_vector_device(rcopy.as<double>(), right.n, d, v->as<double>(), right.restrict_rows.as<int32_t>(),
                                                                        std::max<int64_t>(right.nres, 0), bad, s));
@@ -399,7 +463,7 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
             if (!right.extras.empty()) {
                 if (!lcopied) {
                     B200_TRY(lcopy.alloc(sizeof(double) * left.n * d, s));
-                    B200_CUDA(cudaMemcpyAsync(lcopy.p, left.data.p, sizeof(double) * left.n * d, cudaMemcpyDeviceToDevice, s));
+                    B200_CUDA(cudaMemcpyAsync(lcopy.p, left.rows(), sizeof(double) * left.n * d, cudaMemcpyDeviceToDevice, s));
                     lcopied = true;
                     ldata = lcopy.as<double>();
                 }
@@ -411,6 +475,20 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
         }
         return 0;
     };
+    // B200MNN_MERGE_DEBUG=1: wall-clock per stage (each bracketed by a stream synchronisation), printed at the end
+    const bool dbg = getenv("B200MNN_MERGE_DEBUG") != nullptr;
+    std::vector<std::pair<std::string, double>> stage_s;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_last = now();
+    auto tick = [&](const char* name) {
+        if (!dbg) return;
+        cudaStreamSynchronize(s);
+        const double t = now();
+        for (auto& e : stage_s) if (e.first == name) { e.second += t - t_last; t_last = t; return; }
+        stage_s.emplace_back(name, t - t_last);
+        t_last = t;
+    };
+    tick("upload");
     const bool auto_merge = (merge_left == nullptr || merge_right == nullptr);
     std::vector<int> remainders;                      // node ids still to be merged (auto mode)
     std::vector<std::vector<int64_t>> pairwise;       // lower-triangular counts, [i][j < i]
@@ -447,17 +525,19 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
             return fail(B200MNN_EINVAL, "invalid merge order: a node is merged twice or before it exists");
         Node& L = R.nodes[li];
         Node& Rt = R.nodes[ri];
-        double* ld = L.data.as<double>();
-        double* rd = Rt.data.as<double>();
+        double* ld = L.rows();
+        double* rd = Rt.rows();
         std::vector<double> lold, rold, lnew, rnew;
         if (get_variance) {
             B200_TRY(perbatch_var(L, d, scratch.as<double>(), lold, s));
             B200_TRY(perbatch_var(Rt, d, scratch.as<double>(), rold, s));
         }
+        tick("perbatch_var");
         // orthogonalise each side along the other side's earlier batch vectors (:473-474)
         for (DevBuf* v : L.extras) B200_TRY(correct::center_along_batch_vector_device(rd, Rt.n, d, v->as<double>(), Rt.restrict_rows.as<int32_t>(), std::max<int64_t>(Rt.nres, 0), bad, s));
         for (DevBuf* v : Rt.extras) B200_TRY(correct::center_along_batch_vector_device(ld, L.n, d, v->as<double>(), L.restrict_rows.as<int32_t>(), std::max<int64_t>(L.nres, 0), bad, s));
 
+        tick("orthogonalize");
         // .restricted_mnn
         const int64_t nL = L.nres >= 0 ? L.nres : L.n, nR = Rt.nres >= 0 ? Rt.nres : Rt.n;
         DevBuf first, second;
@@ -465,6 +545,7 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
         B200_TRY(find_pairs(ld, L, rd, Rt, &first, &second, &np));
         if (np == 0) return fail(B200MNN_EINVAL, "no MNN pairs found between the batches being merged");
 
+        tick("mnn_search");
         // correction vectors, overall batch vector, magnitude
         const int64_t acap = std::min<int64_t>(np, Rt.n);
         DevBuf averaged, uniq, dnm;
@@ -479,14 +560,11 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
         DevBuf* overall = new DevBuf();
         R.vec_pool.push_back(overall);
         B200_TRY(overall->alloc(sizeof(double) * d, s));
-        B200_TRY(gemm::col_mean(averaged.as<double>(), d, nmnn, d, overall->as<double>(), s));
+        B200_TRY(col_moment<0>(averaged.as<double>(), nmnn, d, nullptr, 1.0 / (double)nmnn, overall->as<double>(), s));   // colMeans(averaged) (:481)
         bool do_correct = true;
         if (!std::isnan(min_batch_skip)) {
             double* sq = scratch.as<double>();   // [d] mean of squares, then two scalars
-            B200_CUDA(cudaMemsetAsync(sq, 0, sizeof(double) * (d + 2), s));
-            dim3 grid((unsigned)ceil_div(d, 256), (unsigned)ceil_div(nmnn, 1024));
-            col_moment_kernel<1><<<grid, 256, 0, s>>>(averaged.as<double>(), nmnn, d, nullptr, 1.0 / (double)nmnn, sq);
-            B200_LAUNCH_CHECK();
+            B200_TRY(col_moment<1>(averaged.as<double>(), nmnn, d, nullptr, 1.0 / (double)nmnn, sq, s));
             sum_vec_kernel<<<1, 1, 0, s>>>(sq, d, sq + d);
             B200_LAUNCH_CHECK();
             sumsq_vec_kernel<<<1, 1, 0, s>>>(overall->as<double>(), d, sq + d + 1);
@@ -498,6 +576,7 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
             R.batch_size[m] = mag;
             if (mag < min_batch_skip) { do_correct = false; R.skipped[m] = 1; }
         }
+        tick("average_magnitude");
         DevBuf newright;
         if (do_correct) {
             B200_TRY(correct::center_along_batch_vector_device(ld, L.n, d, overall->as<double>(), L.restrict_rows.as<int32_t>(), std::max<int64_t>(L.nres, 0), bad, s));
@@ -508,6 +587,7 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
             }
             B200_TRY(correct::average_correction_device(ld, L.n, rd, Rt.n, d, first.as<int32_t>(), second.as<int32_t>(), np, averaged.as<double>(),
                                                         uniq.as<int32_t>(), dnm.as<int64_t>(), bad, s));
+            tick("center_reaverage");
             // .tricube_weighted_correction: all right cells among the MNN cells of the right node
             const int kk = (int)std::min<int64_t>(std::min<int64_t>(choose_k(k, prop_k, Rt.n), Rt.n), nmnn);
             DevBuf sub, idx, dist;
@@ -525,6 +605,7 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
             B200_TRY(perbatch_var(L, d, scratch.as<double>(), lnew, s));
             B200_TRY(perbatch_var(Rt, d, scratch.as<double>(), rnew, s));
         }
+        tick("tricube");
         if (get_variance) {
             for (int b = 0; b < nb; ++b) R.lost_var[(size_t)m * nb + b] = 0.0;
             for (size_t i = 0; i < L.index.size(); ++i) R.lost_var[(size_t)m * nb + L.index[i]] = 1.0 - lnew[i] / lold[i];
@@ -544,12 +625,18 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
             B200_CUDA(cudaMemcpyAsync(R.pr[m].data(), tmp.p, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, s));
             B200_CUDA(cudaStreamSynchronize(s));
         }
+        tick("pairs_to_host");
         // the new node: rbind(left, right) (:520-525)
         Node& N = R.nodes[nb + m];
         N.n = L.n + Rt.n;
-        B200_TRY(N.data.alloc(sizeof(double) * N.n * d, s));
-        B200_CUDA(cudaMemcpyAsync(N.data.p, ld, sizeof(double) * L.n * d, cudaMemcpyDeviceToDevice, s));
-        B200_CUDA(cudaMemcpyAsync(N.data.as<double>() + L.n * d, rd, sizeof(double) * Rt.n * d, cudaMemcpyDeviceToDevice, s));
+        if (L.ptr && Rt.ptr && L.ptr + L.n * d == Rt.ptr) {   // neighbours in the arena: the new node is the joint window
+            N.ptr = L.ptr;
+            if (rd != Rt.ptr) B200_CUDA(cudaMemcpyAsync(Rt.ptr, rd, sizeof(double) * Rt.n * d, cudaMemcpyDeviceToDevice, s));   // tricube output back in place
+        } else {
+            B200_TRY(N.data.alloc(sizeof(double) * N.n * d, s));
+            B200_CUDA(cudaMemcpyAsync(N.data.p, ld, sizeof(double) * L.n * d, cudaMemcpyDeviceToDevice, s));
+            B200_CUDA(cudaMemcpyAsync(N.data.as<double>() + L.n * d, rd, sizeof(double) * Rt.n * d, cudaMemcpyDeviceToDevice, s));
+        }
         if (L.nres >= 0 || Rt.nres >= 0) {   // .combine_restrict (:610-622)
             N.nres = nL + nR;
             B200_TRY(N.restrict_rows.alloc(sizeof(int32_t) * N.nres, s));
@@ -568,6 +655,7 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
         L.data.release(); L.restrict_rows.release(); L.alive = false;
         Rt.data.release(); Rt.restrict_rows.release(); Rt.alive = false;
         R.final_node = nb + m;
+        tick("rbind");
         if (auto_merge && m + 1 < nm) {   // .update_remainders (:205-226)
             std::vector<int> rest;
             std::vector<std::vector<int64_t>> meta;
@@ -591,6 +679,11 @@ int b200mnn_reduced_mnn(const double* const* batches, const int64_t* ncells, int
         }
     }
     if (nm == 0) R.final_node = 0;
+    if (dbg) {
+        fprintf(stderr, "b200mnn_reduced_mnn: %d devices;", (int)ds.devs.size());
+        for (auto& e : stage_s) fprintf(stderr, " %s %.3f s;", e.first.c_str(), e.second);
+        fprintf(stderr, "\n");
+    }
     int hb = 0;
     B200_CUDA(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));
@@ -625,11 +718,11 @@ int b200mnn_result_corrected(const b200mnn_merge_result* res, double* out, int c
     if (col_major) {
         b200::merge::DevBuf t;
         B200_TRY(t.alloc(sizeof(double) * nd.n * R.d, s));
-        B200_TRY(correct::transpose_device<double>(nd.data.as<double>(), R.d, nd.n, t.as<double>(), s));   // row-major [n x d] == column-major [d x n]
+        B200_TRY(correct::transpose_device<double>(nd.rows(), R.d, nd.n, t.as<double>(), s));   // row-major [n x d] == column-major [d x n]
         B200_CUDA(cudaMemcpyAsync(out, t.p, sizeof(double) * nd.n * R.d, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));
     } else {
-        B200_CUDA(cudaMemcpyAsync(out, nd.data.p, sizeof(double) * nd.n * R.d, cudaMemcpyDeviceToHost, s));
+        B200_CUDA(cudaMemcpyAsync(out, nd.rows(), sizeof(double) * nd.n * R.d, cudaMemcpyDeviceToHost, s));
         B200_CUDA(cudaStreamSynchronize(s));
     }
     return 0;
