@@ -112,7 +112,7 @@ SEXP _batchelor_b200_find_mutual_nn(SEXP data1, SEXP data2, SEXP k1, SEXP k2) {
  * Returns list(corrected [ncells x d] in final node order, node_order, node_ncells, pairs = list of list(left, right)
  * (1-based rows within the merged nodes), batch_size, skipped, lost_var [(nb-1) x nb], merge_left, merge_right). */
 SEXP _batchelor_b200_reduced_mnn(SEXP batches, SEXP merge_left, SEXP merge_right, SEXP k, SEXP prop_k, SEXP ndist, SEXP min_batch_skip,
-                                 SEXP restrict, SEXP get_variance) {
+                                 SEXP restrict_, SEXP get_variance) {
     const int nb = (int) XLENGTH(batches);
     if (nb < 1) Rf_error("at least one batch must be supplied");
     const double** ptr = (const double**) R_alloc(nb, sizeof(double*));
@@ -126,8 +126,8 @@ SEXP _batchelor_b200_reduced_mnn(SEXP batches, SEXP merge_left, SEXP merge_right
         if (Rf_ncols(m) != d) Rf_error("number of columns is not the same across batches");
         ptr[b] = REAL(m); ncells[b] = Rf_nrows(m);
         rptr[b] = NULL; rn[b] = 0;
-        if (!Rf_isNull(restrict) && !Rf_isNull(VECTOR_ELT(restrict, b))) {
-            SEXP r = PROTECT(as_int(VECTOR_ELT(restrict, b))); ++nprot;
+        if (!Rf_isNull(restrict_) && !Rf_isNull(VECTOR_ELT(restrict_, b))) {
+            SEXP r = PROTECT(as_int(VECTOR_ELT(restrict_, b))); ++nprot;
             rptr[b] = (const int32_t*) INTEGER(r); rn[b] = XLENGTH(r);
         }
     }
@@ -136,7 +136,7 @@ SEXP _batchelor_b200_reduced_mnn(SEXP batches, SEXP merge_left, SEXP merge_right
     check(b200mnn_reduced_mnn(ptr, ncells, nb, d, /*col_major=*/1, automerge ? NULL : (const int32_t*) INTEGER(merge_left),
                               automerge ? NULL : (const int32_t*) INTEGER(merge_right), Rf_asInteger(k),
                               Rf_isNull(prop_k) ? -1.0 : Rf_asReal(prop_k), Rf_asReal(ndist), Rf_asReal(min_batch_skip) /* NA_real_ is a NaN */,
-                              Rf_isNull(restrict) ? NULL : rptr, rn, Rf_asLogical(get_variance), &res));
+                              Rf_isNull(restrict_) ? NULL : rptr, rn, Rf_asLogical(get_variance), &res));
     const int nm = nb - 1;
     const int64_t ntotal = b200mnn_result_ncells(res);
     SEXP corrected = PROTECT(Rf_allocMatrix(REALSXP, (int) ntotal, d)); ++nprot;
