@@ -136,10 +136,7 @@ wide_rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, i
                    const int32_t* __restrict__ cand, const float* __restrict__ thr, const double* __restrict__ qnorm2 /* centred */,
                    double inv_s2, double eps_q /* per unit |q| */, double eps_0, int32_t* __restrict__ out_idx,
                    double* __restrict__ out_dist, int* __restrict__ flag_count, int32_t* __restrict__ flag_list, double* __restrict__ flag_dk2) {
-    extern __shared__ unsigned char wsm[];
-    double* cd = reinterpret_cast<double*>(wsm);                 // [np2]
-    int* ci = reinterpret_cast<int*>(cd + WIDE_MAX_KEEP);        // [np2]
-    __shared__ double stage[4][32][17];
+    extern __shared__ __align__(16) unsigned char wsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t jq = blockIdx.x;          // row of the chunk
     const int64_t q = q0 + jq;
@@ -147,18 +144,27 @@ wide_rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, i
     const double* qv = Q + q * d;
     int np2 = 32;
     while (np2 < keep) np2 <<= 1;
-    for (int base = warp * 32; base < np2; base += 128) {
+    const int nthreads = (int)blockDim.x;   // min(128, np2): no idle warps for the usual 64 candidates
+    // dynamic shared memory sized to the launch: [warps][32][17] staging + np2 (distance, id) pairs -> ~9.5 KB for 64
+    // candidates, so that two dozen CTAs share an SM (the gather is latency-bound: occupancy is what hides it)
+    double (*stage)[32][17] = reinterpret_cast<double (*)[32][17]>(wsm);
+    double* cd = reinterpret_cast<double*>(wsm) + (size_t)(nthreads >> 5) * 32 * 17;   // [np2]
+    int* ci = reinterpret_cast<int*>(cd + np2);                                        // [np2]
+    for (int base = warp * 32; base < np2; base += nthreads) {
         const int c = base + lane;
         const int id = (c < keep) ? cand[jq * keep + c] : -1;
         double acc = 0.0;
         for (int t0 = 0; t0 < d; t0 += 16) {
             const int len = min(16, d - t0);
             const int sub = lane & 15, hw = lane >> 4;
-#pragma unroll 4
+            double v[16];   // 16 independent loads in flight per lane (the gather is latency-bound)
+#pragma unroll
             for (int rr = 0; rr < 16; ++rr) {
                 const int rid = __shfl_sync(0xffffffffu, id, 2 * rr + hw);
-                if (sub < len) stage[warp][2 * rr + hw][sub] = (rid >= 0) ? X[(int64_t)rid * d + t0 + sub] : 0.0;
+                v[rr] = (rid >= 0 && sub < len) ? X[(int64_t)rid * d + t0 + sub] : 0.0;
             }
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) stage[warp][2 * rr + hw][sub] = v[rr];
             __syncwarp();
             for (int t = 0; t < len; ++t) {
                 const double df = __dsub_rn(qv[t0 + t], stage[warp][lane][t]);
@@ -172,7 +178,7 @@ wide_rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, i
     __syncthreads();
     for (int size = 2; size <= np2; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < np2 / 2; i += 128) {
+            for (int i = threadIdx.x; i < np2 / 2; i += nthreads) {
                 const int a = (i / stride) * (stride * 2) + (i % stride);
                 const int b = a + stride;
                 const bool up = ((a & size) == 0);
@@ -184,7 +190,7 @@ wide_rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, i
             __syncthreads();
         }
     }
-    for (int j = threadIdx.x; j < k; j += 128) {
+    for (int j = threadIdx.x; j < k; j += nthreads) {
         out_idx[q * k + j] = (ci[j] == 0x7fffffff) ? -1 : ci[j];
         if (out_dist) out_dist[q * k + j] = sqrt(cd[j]);
     }
@@ -269,7 +275,10 @@ int query_knn_wide(const double* dX, int64_t n, const double* dQ, int64_t nq, in
     const double eps_q = 2.0 * (2.0 * c1 * M) + 2.0 * 1.1920928955078125e-07 * 2.0 * M;   // safety factor 2 on the derived bound
     const double eps_0 = 2.0 * 1.1920928955078125e-07 * nm[0] + 1e-12 * (nm[0] + nm[1]);
 
-    const size_t rr_smem = (size_t)WIDE_MAX_KEEP * (sizeof(double) + sizeof(int));
+    int rr_threads = 32, rr_np2 = 32;
+    while (rr_threads < keep && rr_threads < 128) rr_threads <<= 1;
+    while (rr_np2 < keep) rr_np2 <<= 1;
+    const size_t rr_smem = (size_t)(rr_threads / 32) * 32 * 17 * sizeof(double) + (size_t)rr_np2 * (sizeof(double) + sizeof(int));
     B200_CUDA(cudaFuncSetAttribute(wide_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
         const int64_t nr = std::min(chunk, nq - q0);
@@ -285,7 +294,7 @@ int query_knn_wide(const double* dX, int64_t n, const double* dQ, int64_t nq, in
         B200_TRY(gemm_split(Qv, Xop, 3, EPI_SCORE, ep, chain_boxes, stream));
         wide_select_kernel<<<(unsigned)nr, 256, 0, stream>>>(Sbuf, ldS, n, keep, cand, thr);
         B200_LAUNCH_CHECK();
-        wide_rerank_kernel<<<(unsigned)nr, 128, rr_smem, stream>>>(dX, dQ, q0, nr, d, k, keep, cand, thr, qnorm, 1.0 / s2, eps_q, eps_0, d_idx, d_dist,
+        wide_rerank_kernel<<<(unsigned)nr, rr_threads, rr_smem, stream>>>(dX, dQ, q0, nr, d, k, keep, cand, thr, qnorm, 1.0 / s2, eps_q, eps_0, d_idx, d_dist,
                                                                   flag_count, flag_list, flag_dk2);
         B200_LAUNCH_CHECK();
     }

@@ -290,12 +290,12 @@ __global__ void widen_rows_kernel(const float* __restrict__ in, int64_t ld, int6
 // fp64 re-evaluation of sample rows / sample densities (difference-form distances), compared with the tensor result.
 // blocks [0, nrow_s): output rows of cells sample_cells[b]; blocks [nrow_s, nrow_s + ndens_s): densities of MNN cells.
 // err[0] = max over sampled rows of max_g |ref - out| / max_g |ref| (double bits), err[1] = max |dens_ref - dens|.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 smooth_check_kernel(const double* __restrict__ averaged, int64_t G, int64_t nmnn, const int32_t* __restrict__ index0,
                     const double* __restrict__ mat, int64_t Gd, int64_t ncells, double inv_sigma, const double* __restrict__ dens,
                     const double* __restrict__ out, int nrow_s, int ndens_s, double* __restrict__ wbuf /* [nrow_s + ndens_s][nmnn] */,
                     unsigned long long* __restrict__ err) {
-    __shared__ double sm[8];
+    __shared__ double sm[32];
     const int b = blockIdx.x;
     const bool is_row = b < nrow_s;
     const int64_t cell = is_row ? (int64_t)((double)b * (double)(ncells - 1) / (double)max(nrow_s - 1, 1))
@@ -304,7 +304,7 @@ smooth_check_kernel(const double* __restrict__ averaged, int64_t G, int64_t nmnn
     const double* x = mat + cell * Gd;
     double* w = wbuf + (int64_t)b * nmnn;
     double mloc = -INFINITY;
-    for (int64_t i = threadIdx.x; i < nmnn; i += 256) {
+    for (int64_t i = threadIdx.x; i < nmnn; i += blockDim.x) {
         const double* y = mat + (int64_t)index0[i] * Gd;
         double d2 = 0.0;
         for (int64_t g = 0; g < Gd; ++g) { const double df = x[g] - y[g]; d2 = fma(df, df, d2); }
@@ -314,17 +314,17 @@ smooth_check_kernel(const double* __restrict__ averaged, int64_t G, int64_t nmnn
     }
     const double m = block_max(mloc, sm);
     double s = 0.0;
-    for (int64_t i = threadIdx.x; i < nmnn; i += 256) s += exp(w[i] - m);
+    for (int64_t i = threadIdx.x; i < nmnn; i += blockDim.x) s += exp(w[i] - m);
     s = block_sum(s, sm);
     if (!is_row) {
         if (threadIdx.x == 0) atomicMax(&err[1], (unsigned long long)__double_as_longlong(fabs((m + log(s)) - dens[dens_i])));
         return;
     }
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < nmnn; i += 256) w[i] = exp(w[i] - m) / s;
+    for (int64_t i = threadIdx.x; i < nmnn; i += blockDim.x) w[i] = exp(w[i] - m) / s;
     __syncthreads();
     double emax = 0.0, rmax = 0.0;
-    for (int64_t g = threadIdx.x; g < G; g += 256) {
+    for (int64_t g = threadIdx.x; g < G; g += blockDim.x) {
         double acc = 0.0;
         for (int64_t i = 0; i < nmnn; ++i) acc = fma(w[i], averaged[i * G + g], acc);
         emax = fmax(emax, fabs(acc - out[cell * G + g]));
@@ -432,7 +432,7 @@ static int smooth_tensor(const double* d_averaged, int64_t G, int64_t nmnn, cons
     const int nrow_s = (int)std::min<int64_t>(24, ncells), ndens_s = (int)std::min<int64_t>(8, nmnn);
     double* wbuf = ws.get<double>((size_t)(nrow_s + ndens_s) * nmnn);
     if (!ws.ok()) return B200MNN_ENOMEM;
-    smooth_check_kernel<<<nrow_s + ndens_s, 256, 0, stream>>>(d_averaged, G, nmnn, d_index0, d_mat, Gd, ncells, 1.0 / sigma2, dens, d_out, nrow_s,
+    smooth_check_kernel<<<nrow_s + ndens_s, 1024, 0, stream>>>(d_averaged, G, nmnn, d_index0, d_mat, Gd, ncells, 1.0 / sigma2, dens, d_out, nrow_s,
                                                              ndens_s, wbuf, err);
     B200_LAUNCH_CHECK();
     unsigned long long herr[2];

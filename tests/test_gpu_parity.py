@@ -593,3 +593,19 @@ def test_reduced_mnn_auto_merge_matches_oracle():
     for a, b in zip(got.merge_info["pairs"], ref["merge_info"]["pairs"]):
         assert np.array_equal(a["left"], b[0]) and np.array_equal(a["right"], b[1])
     assert np.array_equal(got.batch, ref["batch"]) and _relerr(got.corrected, ref["corrected"]) < RTOL
+
+
+def test_sharded_search_under_nccl():
+    """Hardware parity at N > 1: two ranks over NCCL (query rows sharded, reference replicated, all-gather of the top-k,
+    sharded upload) must reproduce the single-GPU result bit for bit.  Needs two visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the multi-GPU tier and tools/ run it)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(root, "tests", "_dist_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
