@@ -15,6 +15,8 @@ from .api import (  # noqa: F401
     findMutualNN,
     find_mutual_nns,
     mnnCorrect,
+    multiBatchPCA,
+    propagate_to_cells,
     queryKNN,
     reducedMNN,
     smooth_gaussian_kernel,
@@ -22,5 +24,5 @@ from .api import (  # noqa: F401
 
 __all__ = [
     "B200Error", "B200Param", "MNNResult", "SerialParam", "adjust_shift_variance", "cosineNorm", "fastMNN", "findMutualNN",
-    "find_mutual_nns", "mnnCorrect", "queryKNN", "reducedMNN", "smooth_gaussian_kernel", "load", "LIB_PATH",
+    "find_mutual_nns", "mnnCorrect", "multiBatchPCA", "propagate_to_cells", "queryKNN", "reducedMNN", "smooth_gaussian_kernel", "load", "LIB_PATH",
 ]

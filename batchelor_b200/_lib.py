@@ -62,6 +62,7 @@ SIGNATURES = {
     "b200mnn_dev_smooth_gaussian_kernel": [vp, i64, i64, vp, vp, i64, i64, C.c_double, vp, vp],
     "b200mnn_smooth_last_check": [C.POINTER(C.c_int), f64p, f64p],
     "b200mnn_dev_adjust_shift_variance": [vp, i64, vp, i64, i64, vp, C.c_double, vp, i64, vp, i64, vp, vp],
+    "b200mnn_dev_smooth_gaussian_from_centroids": [vp, i64, C.c_int, vp, vp, C.c_int, C.c_double, vp, vp],
     "b200mnn_dev_cosine_norm": [vp, i64, i64, vp, vp, vp],
     "b200mnn_dev_transpose_f64": [vp, i64, i64, vp, vp],
     "b200mnn_dev_debug_candidates": [vp, i64, vp, i64, C.c_int, C.c_int, vp, vp, vp, i64, i64p, vp],

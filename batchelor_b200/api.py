@@ -657,8 +657,87 @@ def reducedMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, ndist=3, 
     return _fast_mnn_core(mats, k, prop_k, restrict, ndist, merge_order, min_batch_skip, auto_merge=auto_merge)
 
 
+def multiBatchPCA(*batches, d=50, subset_row=None, weights=None, get_all_genes=False, get_variance=False, BSPARAM=None, BPPARAM=None):
+    """multiBatchPCA (R/multiBatchPCA.R:211-322, .multi_pca_list) for [genes x cells] matrices: every batch centred on the
+    weighted grand mean of the batch means, scaled by 1/sqrt(ncells/weight) so that each batch contributes equally, exact
+    SVD of the scaled matrix, UNscaled centred batches projected on its left singular vectors.
+
+    Returns ``(pcs, meta)``: ``pcs[b]`` is [cells x d]; ``meta`` has ``rotation`` [genes x d], ``centers`` and, with
+    ``get_variance``, ``var_explained`` (d^2 / nbatches, :420) and ``var_total``.  Rotation columns are sign-normalised
+    (largest |component| positive); an SVD leaves the sign free, the reference's LAPACK call included.
+
+    B200 form (a front end of the hot path, not part of it): the G x G Gram matrix of the scaled
+    data and the projections are fp64 GEMMs and the eigen-decomposition is cuSOLVER's, all through torch -- library code
+    by design here; exact (ExactParam) semantics, no randomised SVD.  ``weights``: None/True (equal), False (by cell
+    count) or one number per batch; tree-like weights are not supported."""
+    import torch
+
+    from . import device as dev
+
+    _check_bpparam(BPPARAM)
+    dev.require_cuda()
+    cuda = torch.device("cuda", torch.cuda.current_device())
+    mats = [np.asarray(b, dtype=np.float64) for b in batches]
+    if len(mats) == 0:
+        raise ValueError("at least one batch must be supplied")
+    G = mats[0].shape[0]
+    for m in mats:
+        if m.ndim != 2 or m.shape[0] != G:
+            raise ValueError("number of rows is not the same across batches")
+    ncells = np.array([m.shape[1] for m in mats], dtype=np.float64)
+    if weights is None or weights is True:
+        w = np.ones(len(mats))
+    elif weights is False:
+        w = ncells.copy()
+    elif isinstance(weights, (list, tuple, np.ndarray)) and not any(isinstance(x, (list, tuple)) for x in weights):
+        w = np.asarray(weights, dtype=np.float64)
+        if w.size != len(mats):
+            raise ValueError("'length(weights)' should be the same as number of entries in '...'")
+    else:
+        raise NotImplementedError("tree-like 'weights' are not supported")
+    keep = None if subset_row is None else _subset_to_index(subset_row, G) - 1
+    dev_mats = [torch.from_numpy(np.ascontiguousarray(m.T)).to(cuda) for m in mats]           # [cells x genes]
+
+    def process(cols):
+        sub = [x if cols is None else x.index_select(1, torch.from_numpy(cols).to(cuda)) for x in dev_mats]
+        centers = sum(x.mean(dim=0) * wi for x, wi in zip(sub, w)) / float(w.sum())        # grand average of batch centres (:268-281)
+        centred = [x - centers for x in sub]
+        scaled = [c / math.sqrt(n / wi) for c, n, wi in zip(centred, ncells, w)]             # (:307-313)
+        return centers, centred, scaled
+
+    centers, centred, scaled = process(keep)
+    nsel = centred[0].shape[1]
+    d_eff = int(min(d, nsel, int(ncells.sum())))
+    gram = sum(sc.T @ sc for sc in scaled)                                                   # [genes x genes]
+    evals, evecs = torch.linalg.eigh(gram)
+    order = torch.argsort(evals, descending=True)[:d_eff]
+    u = evecs.index_select(1, order)
+    sv2 = torch.clamp(evals.index_select(0, order), min=0.0)
+    piv = torch.argmax(u.abs(), dim=0)
+    u = u * torch.sign(u[piv, torch.arange(d_eff, device=cuda)])[None, :]
+    pcs = [(c @ u).cpu().numpy() for c in centred]                                           # crossprod(centered, u) (:238-240)
+    rotation, all_centers = u, centers
+    if get_all_genes and keep is not None:                                                   # .make_pca_metadata (:393-412)
+        rest = np.setdiff1d(np.arange(G), keep)
+        lc, _, lscaled = process(rest)
+        # leftover.u = left.scaled %*% v / d with v = t(scaled) u / d  ->  (sum_b lscaled_b^T scaled_b) u / d^2
+        cross = sum(ls.T @ sc for ls, sc in zip(lscaled, scaled))
+        left_u = (cross @ u) / sv2[None, :]
+        rotation = torch.zeros((G, d_eff), dtype=torch.float64, device=cuda)
+        rotation[torch.from_numpy(keep).to(cuda)] = u
+        rotation[torch.from_numpy(rest).to(cuda)] = left_u
+        all_centers = torch.zeros(G, dtype=torch.float64, device=cuda)
+        all_centers[torch.from_numpy(keep).to(cuda)] = centers
+        all_centers[torch.from_numpy(rest).to(cuda)] = lc
+    meta = {"rotation": rotation.cpu().numpy(), "centers": all_centers.cpu().numpy()}
+    if get_variance:
+        meta["var_explained"] = (sv2 / len(mats)).cpu().numpy()
+        meta["var_total"] = float(sum((sc ** 2).sum() for sc in scaled).item()) / len(mats)
+    return pcs, meta
+
+
 def fastMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, cos_norm=True, ndist=3, d=50, merge_order=None,
-            auto_merge=False, min_batch_skip=0, BNPARAM=None, BPPARAM=None) -> MNNResult:
+            auto_merge=False, min_batch_skip=0, subset_row=None, weights=None, get_variance=False, BNPARAM=None, BPPARAM=None) -> MNNResult:
     """fastMNN (R/fastMNN.R:283-331) for [genes x cells] matrices: cosineNorm -> multi-batch PCA -> reducedMNN.
 
     The PCA front end (R/multiBatchPCA.R) is outside the accelerated path; here it is an
@@ -669,23 +748,20 @@ def fastMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, cos_norm=Tru
     if len(mats) == 1:
         parts, reorder, restricted, _ = _divide_into_batches(mats[0], batch, False, None if restrict is None else restrict[0])
         out = fastMNN(*parts, k=k, prop_k=prop_k, restrict=restricted, cos_norm=cos_norm, ndist=ndist, d=d, merge_order=merge_order,
-                      auto_merge=auto_merge, min_batch_skip=min_batch_skip, BNPARAM=BNPARAM, BPPARAM=BPPARAM)
+                      auto_merge=auto_merge, min_batch_skip=min_batch_skip, subset_row=subset_row, weights=weights,
+                      get_variance=get_variance, BNPARAM=BNPARAM, BPPARAM=BPPARAM)
         out.corrected = out.corrected[reorder - 1]
         out.batch = out.batch[reorder - 1]
         out.merge_info["pairs"] = _reindex_pairings(out.merge_info["pairs"], reorder)
         return out
-    if cos_norm:
-        mats = [cosineNorm(m) for m in mats]
-    # equal-weight multi-batch PCA: centre on the mean of batch means, scale each batch by 1/sqrt(ncells)
-    centre = np.mean([m.mean(axis=1) for m in mats], axis=0)
-    scaled = np.concatenate([(m - centre[:, None]).T / math.sqrt(m.shape[1]) for m in mats], axis=0)
-    dev_t = torch.from_numpy(scaled).cuda() if torch.cuda.is_available() else torch.from_numpy(scaled)
-    _, _, vh = torch.linalg.svd(dev_t, full_matrices=False)
-    rot = vh[: min(d, vh.shape[0])].T.cpu().numpy()
-    pcs = [(m - centre[:, None]).T @ rot for m in mats]
+    if cos_norm:   # R/fastMNN.R:349-350: cosine normalisation over the selected genes
+        mats = [cosineNorm(m, subset_row=subset_row) for m in mats]
+        subset_row = None
+    pcs, meta = multiBatchPCA(*mats, d=d, subset_row=subset_row, weights=weights, get_variance=get_variance, BPPARAM=BPPARAM)   # :353
     out = reducedMNN(*pcs, k=k, prop_k=prop_k, restrict=restrict, ndist=ndist, merge_order=merge_order, auto_merge=auto_merge,
                      min_batch_skip=min_batch_skip, BNPARAM=BNPARAM, BPPARAM=BPPARAM)
-    out.merge_info["rotation"] = rot
+    out.merge_info["rotation"] = meta["rotation"]
+    out.merge_info["pca"] = meta
     return out
 
 
@@ -834,3 +910,27 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
         res.batch = res.batch[reorder - 1]
         res.merge_info["pairs"] = _reindex_pairings(res.merge_info["pairs"], reorder)
     return res
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clusterMNN's propagation step (R/clusterMNN.R:244-312) -- SURVEY.md section 8f, N4
+# ----------------------------------------------------------------------------------------------------------
+def propagate_to_cells(cells, centroids, corrected_centroids, restrict=None, BNPARAM=None, BPPARAM=None):
+    """.propagate_to_cells for one batch in PC space (R/clusterMNN.R:267-283): `cells` [ncells x d] (already projected),
+    `centroids` [nc x d] and their MNN-corrected positions.  sigma = median distance of the (restricted) cells to their
+    nearest centroid (exact search, k = 1); returns cells + Gaussian-weighted centroid corrections."""
+    import torch
+
+    from . import device as dev
+
+    _check_bpparam(BPPARAM)
+    _select_device(BNPARAM)
+    dev.require_cuda()
+    cuda = torch.device("cuda", torch.cuda.current_device())
+    x = torch.from_numpy(np.ascontiguousarray(cells, dtype=np.float64)).to(cuda)
+    cen = torch.from_numpy(np.ascontiguousarray(centroids, dtype=np.float64)).to(cuda)
+    delta = torch.from_numpy(np.ascontiguousarray(corrected_centroids, dtype=np.float64)).to(cuda) - cen
+    q = x if restrict is None else x.index_select(0, torch.from_numpy(_subset_to_index(restrict, x.shape[0]) - 1).to(cuda))
+    _, dist = dev.query_knn(cen, q, 1, want_dist=True)
+    sigma = float(np.median(dist[:, 0].cpu().numpy()))     # stats::median on the host, as the reference does
+    return dev.smooth_gaussian_from_centroids(x, cen, delta, sigma).cpu().numpy()

@@ -321,10 +321,63 @@ int cosine_norm_device(const double* d_x, int64_t n, int64_t G, double* d_out, d
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// clusterMNN's propagation of centroid corrections to cells: .smooth_gaussian_from_centroids (R/clusterMNN.R:289-312)
+// ------------------------------------------------------------------------------------------------
+// out[c,] = x[c,] + sum_j softmax_j(-||x_c - centre_j||^2 / sigma^2) * delta[j,]: a small-K variant of the Gaussian
+// smoothing (tens of centroids, no density term, two-pass soft-max against the row maximum as the reference does).
+// One warp per cell; centres and deltas are read through L1/L2 (a few KB); HBM-bound on x and out.
+__global__ void __launch_bounds__(256)
+centroid_smooth_kernel(const double* __restrict__ x, int64_t n, int d, const double* __restrict__ centers, const double* __restrict__ delta,
+                       int nc, double inv_sigma2, double* __restrict__ out) {
+    extern __shared__ double wsm[];   // [warps][nc] log-weights
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (c >= n) return;
+    double* w = wsm + (size_t)warp * nc;
+    const double* xc = x + c * d;
+    double top = -INFINITY;
+    for (int j = lane; j < nc; j += 32) {
+        double d2 = 0.0;
+        for (int t = 0; t < d; ++t) { const double df = xc[t] - centers[(int64_t)j * d + t]; d2 += df * df; }   // colSums order
+        const double l = -d2 * inv_sigma2;
+        w[j] = l;
+        top = fmax(top, l);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, o));
+    __syncwarp();
+    double total = 0.0;
+    for (int j = 0; j < nc; ++j) total += exp(w[j] - top);   // rowSums order, identical on every lane
+    for (int t = lane; t < d; t += 32) {
+        double acc = xc[t];
+        for (int j = 0; j < nc; ++j) acc += (exp(w[j] - top) / total) * delta[(int64_t)j * d + t];   // x + outer(norm.weights[,j], delta[j,]) in j order
+        out[c * d + t] = acc;
+    }
+}
+
+int centroid_smooth_device(const double* d_x, int64_t n, int d, const double* d_centers, const double* d_delta, int nc, double sigma,
+                           double* d_out, cudaStream_t stream) {
+    B200_TRY(ensure_device());
+    if (n <= 0 || d <= 0) return 0;
+    if (nc < 1) return fail(B200MNN_EINVAL, "at least one centroid is needed");
+    if ((size_t)nc * 8 * sizeof(double) > (size_t)160 * 1024) return fail(B200MNN_EINVAL, "too many centroids for the propagation kernel");
+    const size_t smem = (size_t)8 * nc * sizeof(double);
+    if (smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(centroid_smooth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    centroid_smooth_kernel<<<(unsigned)ceil_div(n, 8), 256, smem, stream>>>(d_x, n, d, d_centers, d_delta, nc, 1.0 / (sigma * sigma), d_out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace correct
 }  // namespace b200
 
 extern "C" {
+
+int b200mnn_dev_smooth_gaussian_from_centroids(const double* d_x, int64_t n, int d, const double* d_centers, const double* d_delta, int nc,
+                                               double sigma, double* d_out, void* stream) {
+    return b200::correct::centroid_smooth_device(d_x, n, d, d_centers, d_delta, nc, sigma, d_out, static_cast<cudaStream_t>(stream));
+}
 
 int b200mnn_dev_average_correction(const double* d_ref, int64_t n1, const double* d_cur, int64_t n2, int d, const int32_t* d_first,
                                    const int32_t* d_second, int64_t np, double* d_averaged, int32_t* d_second_unique, int64_t* d_nmnn,

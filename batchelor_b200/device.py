@@ -287,3 +287,13 @@ def adjust_shift_variance(data1: torch.Tensor, data2: torch.Tensor, vect: torch.
               float(sigma2), _p(r1), r1.shape[0], _p(r2), r2.shape[0], _p(out), _stream())
     _count(3)
     return out
+
+
+def smooth_gaussian_from_centroids(x: torch.Tensor, centers: torch.Tensor, delta: torch.Tensor, sigma: float) -> torch.Tensor:
+    """x [n,d] + soft-max-weighted centroid corrections (R/clusterMNN.R:289-312): centers, delta [nc,d]."""
+    x = _f64(x); centers = _f64(centers); delta = _f64(delta)
+    out = torch.empty_like(x)
+    _lib.call("b200mnn_dev_smooth_gaussian_from_centroids", _p(x), x.shape[0], x.shape[1], _p(centers), _p(delta), centers.shape[0], float(sigma),
+              _p(out), _stream())
+    _count(1)
+    return out

@@ -205,6 +205,12 @@ int b200mnn_dev_adjust_shift_variance(const double* d_data1, int64_t n1, const d
                                       const double* d_vect, double sigma2, const int32_t* d_r1, int64_t nr1,
                                       const int32_t* d_r2, int64_t nr2, double* d_out, void* stream);
 
+/* clusterMNN's propagation of centroid corrections to cells, .smooth_gaussian_from_centroids (R/clusterMNN.R:289-312):
+ * d_out[c,] = d_x[c,] + sum_j softmax_j(-||x_c - centre_j||^2 / sigma^2) delta[j,].  d_x, d_out [n x d], d_centers, d_delta
+ * [nc x d], row-major device matrices (the small-K variant of the Gaussian smoothing). */
+int b200mnn_dev_smooth_gaussian_from_centroids(const double* d_x, int64_t n, int d, const double* d_centers, const double* d_delta, int nc,
+                                               double sigma, double* d_out, void* stream);
+
 /* Cosine normalisation on device: d_x [n x G] row-major (one cell contiguous); d_out may alias d_x or be NULL. */
 int b200mnn_dev_cosine_norm(const double* d_x, int64_t n, int64_t G, double* d_out, double* d_l2, void* stream);
 

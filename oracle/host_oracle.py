@@ -447,3 +447,47 @@ def mnn_correct(batches, k=20, prop_k=None, sigma=0.1, cos_norm_in=True, cos_nor
     res = _finish(tree, full, pairings, left_set, right_set, {})
     res["corrected"] = res["corrected"].T
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# R/clusterMNN.R:267-312  sigma + .smooth_gaussian_from_centroids
+# ------------------------------------------------------------------------------------------------
+def smooth_gaussian_from_centroids(x, centers, sigma, delta):
+    x = np.asarray(x, dtype=np.float64)
+    weights = np.stack([-((x - centers[j]) ** 2).sum(axis=1) for j in range(centers.shape[0])], axis=1) / sigma ** 2
+    top = weights.max(axis=1, keepdims=True)
+    nw = np.exp(weights - top)
+    nw /= nw.sum(axis=1, keepdims=True)
+    out = x.copy()
+    for j in range(centers.shape[0]):
+        out = out + np.outer(nw[:, j], delta[j])
+    return out
+
+
+def propagate_to_cells(cells, centroids, corrected_centroids, restrict=None, knn=None):
+    knn = knn or capi.query_knn
+    q = cells if restrict is None else cells[np.asarray(restrict, dtype=np.int64) - 1]
+    _, dist = knn(centroids, q, 1)
+    sigma = float(np.median(dist[:, 0]))
+    return smooth_gaussian_from_centroids(cells, centroids, sigma, corrected_centroids - centroids)
+
+
+# ------------------------------------------------------------------------------------------------
+# R/multiBatchPCA.R:211-322  .multi_pca_list with ExactParam (numpy SVD); rotation sign-normalised like the product
+# ------------------------------------------------------------------------------------------------
+def multi_batch_pca(batches, d=50, weights=None, get_variance=False):
+    mats = [np.asarray(b, dtype=np.float64) for b in batches]
+    ncells = np.array([m.shape[1] for m in mats], dtype=np.float64)
+    w = np.ones(len(mats)) if weights is None else (ncells.copy() if weights is False else np.asarray(weights, dtype=np.float64))
+    centers = sum(m.mean(axis=1) * wi for m, wi in zip(mats, w)) / w.sum()
+    centred = [m - centers[:, None] for m in mats]
+    scaled = np.hstack([c / math.sqrt(n / wi) for c, n, wi in zip(centred, ncells, w)])
+    u, sv, _ = np.linalg.svd(scaled, full_matrices=False)
+    u = u[:, :d]; sv = sv[:d]
+    piv = np.argmax(np.abs(u), axis=0)
+    u = u * np.sign(u[piv, np.arange(u.shape[1])])[None, :]
+    out = {"pcs": [c.T @ u for c in centred], "rotation": u, "centers": centers}
+    if get_variance:
+        out["var_explained"] = sv ** 2 / len(mats)
+        out["var_total"] = float((scaled ** 2).sum()) / len(mats)
+    return out

@@ -609,3 +609,38 @@ def test_sharded_search_under_nccl():
            os.path.join(root, "tests", "_dist_gpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_GPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_propagate_to_cells_matches_oracle():
+    """clusterMNN's propagation (R/clusterMNN.R:267-312): sigma from the exact k = 1 search, Gaussian-weighted centroid deltas."""
+    rng = np.random.default_rng(21)
+    cen = rng.normal(scale=3.0, size=(37, 20))
+    cells = cen[rng.integers(0, 37, size=5000)] + rng.normal(size=(5000, 20))
+    corrected = cen + rng.normal(scale=0.5, size=cen.shape)
+    restrict = np.arange(1, 4001)
+    got = bb.propagate_to_cells(cells, cen, corrected, restrict=restrict)
+    ref = ho.propagate_to_cells(cells, cen, corrected, restrict=restrict)
+    assert _relerr(got, ref) < 1e-12
+
+
+def test_multi_batch_pca_matches_exact_svd():
+    """multiBatchPCA (R/multiBatchPCA.R:211-322) against numpy's exact SVD on data with a clear spectrum: rotation, PCs,
+    centres and variance explained; unequal batch sizes exercise the per-batch scaling and the weights."""
+    rng = np.random.default_rng(4)
+    load = rng.normal(size=(8, 300)) * np.linspace(6.0, 1.5, 8)[:, None]
+    mats = [(rng.normal(size=(n, 8)) @ load + 0.3 * rng.normal(size=(n, 300)) + off).T for n, off in [(400, 0.0), (250, 0.5), (900, -0.2)]]
+    for weights in (None, [1.0, 2.0, 0.5], False):
+        pcs, meta = bb.multiBatchPCA(*mats, d=6, weights=weights, get_variance=True)
+        ref = ho.multi_batch_pca(mats, d=6, weights=weights, get_variance=True)
+        assert _relerr(meta["centers"], ref["centers"]) < 1e-12
+        assert _relerr(meta["rotation"], ref["rotation"]) < 1e-7
+        for a, b in zip(pcs, ref["pcs"]):
+            assert _relerr(a, b) < 1e-7
+        assert np.allclose(meta["var_explained"], ref["var_explained"], rtol=1e-9) and np.isclose(meta["var_total"], ref["var_total"], rtol=1e-9)
+    # get_all_genes: genes outside subset_row get rotation vectors by projection (:393-405); check against the definition
+    keep = np.arange(0, 300, 2) + 1
+    pcs, meta = bb.multiBatchPCA(*mats, d=5, subset_row=keep, get_all_genes=True)
+    sub = ho.multi_batch_pca([m[keep - 1] for m in mats], d=5)
+    assert _relerr(meta["rotation"][keep - 1], sub["rotation"]) < 1e-7 and meta["rotation"].shape == (300, 5)
+    res = bb.fastMNN(*mats, d=6, k=15)
+    assert res.corrected.shape == (1550, 6) and res.merge_info["rotation"].shape == (300, 6)
