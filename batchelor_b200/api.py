@@ -790,8 +790,6 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
 
     _check_bpparam(BPPARAM)
     _select_device(BNPARAM)
-    if auto_merge:
-        raise NotImplementedError("auto.merge=TRUE is not part of the accelerated path yet (SURVEY.md section 8f, N3)")
     if svd_dim:
         raise NotImplementedError("svd.dim > 0 (biological-subspace removal) is outside the accelerated path (default is 0)")
     mats = [np.asarray(b, dtype=np.float64) for b in batches]
@@ -851,10 +849,27 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
             r = torch.from_numpy(np.asarray(restrict[i - 1], dtype=np.int64) - 1).to(cuda)
         return _Node([i], in_b[i - 1], r, extras=[None if same_set else out_b[i - 1]])
 
-    tree = _fill(tree, leaf)
+    def count_pairs(a, b):
+        """.count_mnn_pairs with orthogonalize=FALSE (R/mnnCorrect.R:212): MNN pairs between two nodes."""
+        f, _ = _restricted_mnn(dev, a.data, a.restrict, b.data, b.restrict, k, prop_k)
+        return int(f.numel())
+
+    if auto_merge:   # .initialize_auto_search (R/MNN_tree.R:154-168)
+        remainders = [leaf(i) for i in range(1, nb + 1)]
+        pairwise = np.zeros((nb, nb), dtype=np.int64)
+        for i in range(nb):
+            for j in range(i):
+                pairwise[i, j] = count_pairs(remainders[i], remainders[j])
+    else:
+        tree = _fill(tree, leaf)
     pairings, left_set, right_set = [], [], []
     for _ in range(nb - 1):
-        left, right, path = _next_merge(tree)
+        if auto_merge:   # .pick_best_merge: first maximum in column-major order; row = left, column = right
+            cols, rows = np.nonzero(pairwise.T == pairwise.max())
+            chosen = (int(rows[0]), int(cols[0]))
+            left, right = remainders[chosen[0]], remainders[chosen[1]]
+        else:
+            left, right, path = _next_merge(tree)
         ld, rd = left.data, right.data
         lx, rx = left.extras[0], right.extras[0]
         t0 = time.perf_counter()
@@ -899,7 +914,18 @@ def mnnCorrect(*batches, batch=None, restrict=None, k=20, prop_k=None, sigma=0.1
                      _combine_restrict(ld.shape[0], left.restrict, rd.shape[0], right.restrict, cuda),
                      origin=np.concatenate([left.origin, right.origin]),
                      extras=[None if same_set else torch.cat([lx, new_rx], dim=0)])
-        tree = _update(tree, path, node)
+        if auto_merge:   # .update_remainders (R/MNN_tree.R:205-226)
+            keep = [i for i in range(len(remainders)) if i not in chosen]
+            remainders = [remainders[i] for i in keep]
+            if remainders:
+                old_meta = pairwise[np.ix_(keep, keep)]
+                new_stats = np.array([count_pairs(node, r) for r in remainders], dtype=np.int64)
+                pairwise = np.hstack([np.vstack([old_meta, new_stats[None, :]]), np.zeros((len(keep) + 1, 1), dtype=np.int64)])
+                remainders.append(node)
+            else:
+                tree = node
+        else:
+            tree = _update(tree, path, node)
     t0 = time.perf_counter()
     full = (tree.data if same_set else tree.extras[0]).cpu().numpy()
     res = _finish(tree, full, pairings, left_set, right_set, {})

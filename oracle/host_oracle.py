@@ -390,7 +390,7 @@ def adjust_shift_variance(data1, data2, correction, sigma, subset_row=None, rest
 
 # R/mnnCorrect.R:179-393  .mnn_correct + .mnn_correct_core (svd.dim=0, same gene set in and out, predefined order)
 def mnn_correct(batches, k=20, prop_k=None, sigma=0.1, cos_norm_in=True, cos_norm_out=True, var_adj=True,
-                restrict=None, merge_order=None, knn=None, mutual=None, smooth=None, kernel=None):
+                restrict=None, merge_order=None, knn=None, mutual=None, smooth=None, kernel=None, auto_merge=False):
     """batches: list of [genes x cells].  Returns dict(corrected [genes x cells], batch, merge_info)."""
     batches = [np.asarray(b, dtype=np.float64) for b in batches]
     in_b, out_b = list(batches), list(batches)
@@ -409,19 +409,34 @@ def mnn_correct(batches, k=20, prop_k=None, sigma=0.1, cos_norm_in=True, cos_nor
         same_set = False
     in_t = [b.T.copy() for b in in_b]
     out_t = [b.T.copy() for b in out_b]
-    tree = create_tree_predefined(in_t, restrict, merge_order)
-
     def add_out(t):
         if not isinstance(t, list):
             t.extras = [None if same_set else out_t[t.index[0] - 1]]
             return t
         return [add_out(t[0]), add_out(t[1])]
 
-    tree = add_out(tree)
+    def count_pairs(a, b):   # .count_mnn_pairs with orthogonalize=FALSE (R/mnnCorrect.R:212)
+        return len(restricted_mnn(a.data, a.restrict, b.data, b.restrict, k, prop_k, mutual=mutual)[0])
+
+    nb = len(batches)
+    if auto_merge:   # R/mnnCorrect.R:211-223 + R/MNN_tree.R:154-168
+        remainders = [add_out(Node([i + 1], in_t[i], None if restrict is None else restrict[i])) for i in range(nb)]
+        pairwise = np.zeros((nb, nb), dtype=np.int64)
+        for i in range(nb):
+            for j in range(i):
+                pairwise[i, j] = count_pairs(remainders[i], remainders[j])
+        tree = None
+    else:
+        tree = add_out(create_tree_predefined(in_t, restrict, merge_order))
     nmerges = len(batches) - 1
     pairings, left_set, right_set = [], [], []
     for _ in range(nmerges):
-        left, right, path = get_next_merge(tree)
+        if auto_merge:
+            cols, rows = np.nonzero(pairwise.T == pairwise.max())
+            chosen = (int(rows[0]), int(cols[0]))
+            left, right = remainders[chosen[0]], remainders[chosen[1]]
+        else:
+            left, right, path = get_next_merge(tree)
         ld, rd = left.data, right.data
         lx, rx = left.extras[0], right.extras[0]
         s1, s2 = restricted_mnn(ld, left.restrict, rd, right.restrict, k, prop_k, mutual=mutual)
@@ -442,7 +457,18 @@ def mnn_correct(batches, k=20, prop_k=None, sigma=0.1, cos_norm_in=True, cos_nor
                     combine_restrict(ld.shape[0], left.restrict, rd.shape[0], right.restrict),
                     origin=np.concatenate([left.origin, right.origin]),
                     extras=[None if same_set else np.vstack([lx, rx])])
-        tree = update_tree(tree, path, node)
+        if auto_merge:
+            keep = [i for i in range(len(remainders)) if i not in chosen]
+            remainders = [remainders[i] for i in keep]
+            if remainders:
+                old = pairwise[np.ix_(keep, keep)]
+                new_stats = np.array([count_pairs(node, r) for r in remainders], dtype=np.int64)
+                pairwise = np.hstack([np.vstack([old, new_stats[None, :]]), np.zeros((len(keep) + 1, 1), dtype=np.int64)])
+                remainders.append(node)
+            else:
+                tree = node
+        else:
+            tree = update_tree(tree, path, node)
     full = tree.data if same_set else tree.extras[0]
     res = _finish(tree, full, pairings, left_set, right_set, {})
     res["corrected"] = res["corrected"].T

@@ -644,3 +644,12 @@ def test_multi_batch_pca_matches_exact_svd():
     assert _relerr(meta["rotation"][keep - 1], sub["rotation"]) < 1e-7 and meta["rotation"].shape == (300, 5)
     res = bb.fastMNN(*mats, d=6, k=15)
     assert res.corrected.shape == (1550, 6) and res.merge_info["rotation"].shape == (300, 6)
+
+
+def test_mnn_correct_auto_merge_matches_oracle():
+    """mnnCorrect(auto.merge=TRUE): R/mnnCorrect.R:211-223 (pair counts without orthogonalisation) + R/MNN_tree.R:196-226."""
+    A, B, Cc = synth.gene_batches(3, [220, 260, 200], G=100, latent=5, ncomp=3)
+    got = bb.mnnCorrect(A, B, Cc, k=12, auto_merge=True, sigma=1.0)
+    ref = ho.mnn_correct([A, B, Cc], k=12, auto_merge=True, sigma=1.0)
+    assert got.merge_info["left"] == ref["merge_info"]["left"] and got.merge_info["right"] == ref["merge_info"]["right"]
+    assert np.array_equal(got.batch, ref["batch"]) and _relerr(got.corrected, ref["corrected"]) < RTOL
