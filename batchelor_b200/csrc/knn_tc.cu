@@ -871,7 +871,111 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
     return m;
 }
 
-template <int E, int NBOX>
+// ------------------------------------------------------------------------------------------------
+// Per-thread epilogue of the TS kernel (EPI == 1; lists of 32 candidates per row, i.e. E == 1)
+// ------------------------------------------------------------------------------------------------
+// The replace-the-maximum lists above spend ~25 issue slots per insertion in chains of dependent warp collectives, and
+// with cluster pruning nearly every scored tile belongs to the queries' own component (one insertion per row and tile
+// or so).  Here nothing on the hot path is cooperative and the lists live in REGISTERS:
+//  * every THREAD owns the scores it reads from TMEM (16x32bx2: lanes r and r + 16 hold 64 columns each of row r) and
+//    an ascending list of its SL_KEEP = 24 best scores in as many registers (two threads per row: 48 kept for 32
+//    candidates, enough for every k of E == 1).  A list entry is the order-preserving integer image of the
+//    score with its low 5 bits replaced by a SLOT number; the reference id sits in that slot of a small per-thread table
+//    in shared memory and never moves.  Inserting v is  l[i] = max(l[i-1], min(l[i], v))  for all i -- 46 integer
+//    min/max instructions, no loads, no branches, no dependent chain (a lane with nothing to insert passes v = ~0);
+//    the entry that drops out hands its slot to the new one.  (Measured alternatives: a binary heap in shared memory
+//    needs ~800 cycles per insertion round at two warps per scheduler -- four dependent load-compare-store levels;
+//    a sorted list in shared memory moves 16 KB per round and warp and made the kernel LSU-bound.)
+//  * hot path, per 4 scores: two MINs, one compare, two address computations and three PREDICATED instructions that
+//    push the whole quad as a record (4 scores + id of the first) onto the thread's record stack when its minimum is
+//    below the thread's threshold -- no vote, no branch, no staging.  Store addresses are computed from the record
+//    count into fresh registers: updating one pointer register in place made every store wait for the previous one to
+//    leave the LSU queue (write-after-read on the address register, ~11 cycles per store, measured);
+//  * records are popped by ALL lanes side by side (one record per lane and step); the scores of the record that are
+//    still below the thread's threshold are inserted one per round, smallest first.  A step is taken after a tile when
+//    at least half of the lanes have a record (SIMT efficiency), and before 32 scores are pushed whenever some lane
+//    could run out of room.  Spreading the steps over the tiles matters: all eight warps must have read a tile before
+//    its accumulator stage is recycled, so one warp's long drain stalls the whole pipeline;
+//  * thresholds.  T = l[31] with the slot bits cleared is a lower bound (in the integer image) of every score this
+//    thread ever dropped or refused, and it only decreases.  The thread's filter is min(own T, partner's T) as a float,
+//    refreshed after every step (a stale threshold only admits more records);
+//  * at the end of the stream the two lists of a row are merged (one min/max step across the lanes): the 32 smallest
+//    are the row's candidates and thr = min(both T, smallest dropped entry), so that every scanned reference that is
+//    not a candidate has score >= thr -- the same certificate the re-rank expects.
+constexpr int SL_KEEP = 24;                          // list entries (registers) and id slots per thread (>= the largest k of E == 1)
+constexpr int SL_PREC = 16;                          // record stack entries per thread
+constexpr int SL_ID_BYTES = SL_KEEP * 32 * 4;        // per warp: id of slot s of lane l at [s][l]
+constexpr int SL_RS_BYTES = SL_PREC * 32 * 16;       // record scores (float4 per record and lane)
+constexpr int SL_RI_BYTES = SL_PREC * 32 * 4;        // record ids
+constexpr int SL_WARP_BYTES = SL_ID_BYTES + SL_RS_BYTES + SL_RI_BYTES;
+constexpr uint32_t SL_SLOT_MASK = 31u;
+
+// Pushes the quad (a, b, c, d) = scores of references id0 .. id0 + 3 when its minimum is below thr.
+// cnt: this lane's record count; rs_addr / ri_addr: shared-memory addresses of this lane's record 0 (scores / id).
+__device__ __forceinline__ void sl_push_quad(const float a, const float b, const float c, const float d, const float thr, const uint32_t id0,
+                                             uint32_t& cnt, const uint32_t rs_addr, const uint32_t ri_addr) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f32 m;\n\t.reg .b32 as, ai;\n\t"
+        "min.f32 m, %1, %2, %3;\n\t"
+        "min.f32 m, m, %4;\n\t"
+        "setp.lt.f32 p, m, %5;\n\t"
+        "mad.lo.u32 as, %0, 512, %7;\n\t"
+        "mad.lo.u32 ai, %0, 128, %8;\n\t"
+        "@p st.shared.v4.f32 [as], {%1, %2, %3, %4};\n\t"
+        "@p st.shared.u32 [ai], %6;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t}"
+        : "+r"(cnt)
+        : "f"(a), "f"(b), "f"(c), "f"(d), "f"(thr), "r"(id0), "r"(rs_addr), "r"(ri_addr)
+        : "memory");
+}
+// The 32 scores v[] of references idb ...
+__device__ __forceinline__ void sl_push32(const uint32_t (&v)[32], const float thr, const uint32_t idb, uint32_t& cnt, const uint32_t rs_addr,
+                                          const uint32_t ri_addr) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+        sl_push_quad(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]), thr, idb + i, cnt,
+                     rs_addr, ri_addr);
+}
+// Inserts key v into the ascending register list (v = ~0: nothing happens); the largest entry drops out.
+__device__ __forceinline__ void sl_insert(uint32_t (&l)[SL_KEEP], const uint32_t v) {
+#pragma unroll
+    for (int i = SL_KEEP - 1; i >= 1; --i) l[i] = max(l[i - 1], min(l[i], v));
+    l[0] = min(l[0], v);
+}
+// One step: every lane with a record pops its top record and inserts the scores that are below its threshold.
+// cnt: this lane's record count; ids: this lane's slot table (slot s at ids[s * 32]); all lanes of the warp take part.
+__device__ __forceinline__ void sl_step(uint32_t (&l)[SL_KEEP], uint32_t* ids, const float4* rs, const uint32_t* ri, uint32_t& cnt, const float thr,
+                                        long long* stat) {
+    const bool have = cnt > 0u;
+    const uint32_t j = have ? cnt - 1u : 0u;
+    float4 s = rs[j * 32];
+    const uint32_t id0 = ri[j * 32];
+    const float inf = __int_as_float(0x7f800000);
+    if (!have) s = make_float4(inf, inf, inf, inf);
+    cnt = j;
+    float lim = thr;   // <= own T at all times
+    if (stat) { stat[0] += 1; stat[1] += __popc(__ballot_sync(0xffffffffu, have)); }
+#pragma unroll 1
+    while (true) {
+        const float cm = fminf(fmin3(s.x, s.y, s.z), s.w);
+        const bool act = cm < lim;
+        if (!__any_sync(0xffffffffu, act)) break;
+        if (stat) { stat[3] += 1; stat[4] += __popc(__ballot_sync(0xffffffffu, act)); }
+        const uint32_t q = (cm == s.x) ? 0u : ((cm == s.y) ? 1u : ((cm == s.z) ? 2u : 3u));
+        s.x = (q == 0u) ? inf : s.x;
+        s.y = (q == 1u) ? inf : s.y;
+        s.z = (q == 2u) ? inf : s.z;
+        s.w = (q == 3u) ? inf : s.w;
+        const uint32_t slot = l[SL_KEEP - 1] & SL_SLOT_MASK;          // the entry that drops out hands over its slot
+        const uint32_t key = (ord_bits(cm) & ~SL_SLOT_MASK) | slot;    // < own T (multiple of 32) whenever act
+        if (act) ids[slot * 32] = id0 + q;
+        sl_insert(l, act ? key : 0xFFFFFFFFu);
+        lim = fminf(lim, ord_float(l[SL_KEEP - 1] & ~SL_SLOT_MASK));
+    }
+    __syncwarp();
+}
+
+template <int E, int NBOX, int EPI>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] query operand rows (global); the first NBOX*64 columns are used
                          const int a_pitch,
@@ -896,9 +1000,11 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     constexpr int KEEP = 32 * E;
 
     uint8_t* smB = smem;
-    uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);                             // [8 warps][16 rows][KEEP] (score bits, id)
-    float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 16 * KEEP);                   // [8 warps][8][32]
-    float* thr_s = reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                                // [128] row thresholds
+    // EPI == 0: [8 warps][16 rows][KEEP] (score bits, id) + [8 warps][8][32] float4 staging; EPI == 1: [8 warps][SL_WARP_BYTES]
+    uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);
+    float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 16 * KEEP);
+    float* thr_s = EPI == 1 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * SL_WARP_BYTES)
+                            : reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                     // [128] row thresholds
     volatile int* ring = reinterpret_cast<int*>(thr_s + BM);                                                   // [TS_RING] tile ids, -1 = end
     float* qoff_s = reinterpret_cast<float*>(thr_s + BM) + TS_RING;                                            // [128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(qoff_s + BM);
@@ -964,7 +1070,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                         if (++slot == nslot) { slot = 0; phase ^= 1; }
                         continue;
                     }
-                    mbar_wait(smem_u32(&empty[slot]), phase ^ 1);   // lane 0 only
+                    mbar_wait_parked(smem_u32(&empty[slot]), phase ^ 1);   // lane 0 only
                     if (tile < 0 || dbg_mode == 3) {
                         mbar_arrive(smem_u32(&full[slot]));
                     } else {
@@ -1032,7 +1138,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         for (int tl = mma_id; more; tl += 2) {
             const int stage = tl % TS_STAGES;
             const uint32_t use = (uint32_t)(tl / TS_STAGES);
-            mbar_wait_u(smem_u32(&tempty[stage]), (use & 1) ^ 1);
+            mbar_wait_parked_u(smem_u32(&tempty[stage]), (use & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = acc_base + (uint32_t)(stage * TS_BN);
             const int box0 = tl * NBOX;
@@ -1040,7 +1146,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             uint32_t phase = (uint32_t)((box0 / nslot) & 1);
 #pragma unroll
             for (int b = 0; b < NBOX; ++b) {
-                mbar_wait_u(smem_u32(&full[slot]), phase);
+                mbar_wait_parked_u(smem_u32(&full[slot]), phase);
                 tc_fence_after();
                 if (b == 0 && ring[tl & (TS_RING - 1)] < 0) {   // end marker: pass it on to the epilogue, done
                     if (elect_one()) mbar_arrive(smem_u32(&tfull[stage]));
@@ -1078,8 +1184,10 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         long long acc_t[4] = {0, 0, 0, 0};   // measurement aid (trace only): tfull wait, TMEM load, scan + hits
         long long stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // measurement aid (trace only), see ts_insert_staged
         uint32_t v0[32], v1[32];
+        if constexpr (EPI == 0) {
 #pragma unroll
-        for (int i = 0; i < KEEP / 2; ++i) mylist[i * 32 + lane] = make_uint2(ORD_INF, 0xFFFFFFFFu);   // empty lists: score +inf, id -1
+            for (int i = 0; i < KEEP / 2; ++i) mylist[i * 32 + lane] = make_uint2(ORD_INF, 0xFFFFFFFFu);   // empty lists: score +inf, id -1
+        }
 
         if (grp == 0) {
             // this thread's query row -> TMEM (A operand of every MMA of this CTA); the warp covers the whole lane quarter
@@ -1101,6 +1209,108 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         }
         __syncwarp();
 
+        if constexpr (EPI == 1) {
+            // ---------- per-thread epilogue (see sl_* above) ----------
+            uint8_t* wbase = reinterpret_cast<uint8_t*>(lists) + (size_t)(warp - 2) * SL_WARP_BYTES;
+            uint32_t* ids = reinterpret_cast<uint32_t*>(wbase) + lane;                            // slot s at ids[s * 32]
+            const float4* rs = reinterpret_cast<const float4*>(wbase + SL_ID_BYTES) + lane;       // record j at rs[j * 32]
+            const uint32_t* ri = reinterpret_cast<const uint32_t*>(wbase + SL_ID_BYTES + SL_RS_BYTES) + lane;
+            const uint32_t rs_addr = smem_u32(rs), ri_addr = smem_u32(ri);
+            const float inf = __int_as_float(0x7f800000);
+            uint32_t l[SL_KEEP];   // ascending keys: (order image of the score & ~31) | slot; empty = image of +inf
+#pragma unroll
+            for (int i = 0; i < SL_KEEP; ++i) {
+                l[i] = ORD_INF | (uint32_t)i;
+                ids[i * 32] = 0xFFFFFFFFu;   // id -1
+            }
+            __syncwarp();
+            uint32_t cnt = 0;    // records on this lane's stack
+            float thr = inf;     // min(own T, partner's T) as a float: what a score must beat to be recorded
+            int seq = 0, stage = 0;
+            uint32_t par = 0;
+            auto step = [&]() {
+                long long td = 0;
+                if (trace) td = clock64();
+                sl_step(l, ids, rs, ri, cnt, thr, trace ? stat : nullptr);
+                const float own = ord_float(l[SL_KEEP - 1] & ~SL_SLOT_MASK);
+                thr = fminf(own, __shfl_xor_sync(0xffffffffu, own, 16));
+                if (lane < 16) thr_pub[lane] = thr;
+                if (trace) acc_t[3] += clock64() - td;
+            };
+            while (true) {
+                long long c0 = 0, c1 = 0, c2 = 0;
+                if (trace) c0 = clock64();
+                mbar_wait_u(smem_u32(&tfull[stage]), par);
+                tc_fence_after();
+                const int tile = ring[seq & (TS_RING - 1)];
+                if (tile < 0) break;
+                if (trace) c1 = clock64();
+                const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
+                tmem_ld16x2(tbase, v0);
+                tmem_ld16x2(tbase + 64u, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
+                ++seq;
+                if (trace) { c2 = clock64(); acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; }
+                if (dbg_mode == 1) continue;
+                const uint32_t idb = (uint32_t)tile * (uint32_t)TS_BN + (uint32_t)(lane >> 4) * 32u;   // reference of v0[0]; v1[0] is 64 further
+                // ONE copy of the step code (the loop is not unrolled); 32 scores = 8 quads need room for 8 records
+#pragma unroll 1
+                for (int h = 0; h < 3; ++h) {
+                    // before a push: steps until every lane has room; after the tile: one step if at least half of the
+                    // lanes have a record (worth it)
+                    bool need = (h < 2) ? __any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 8))
+                                        : (__popc(__ballot_sync(0xffffffffu, cnt != 0u)) >= 16);
+                    while (need) {
+                        step();
+                        need = (h < 2) && __any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 8));
+                    }
+                    if (h == 0) sl_push32(v0, thr, idb, cnt, rs_addr, ri_addr);
+                    else if (h == 1) sl_push32(v1, thr, idb + 64u, cnt, rs_addr, ri_addr);
+                }
+                if (trace) acc_t[2] += clock64() - c2;   // includes the steps (acc_t[3])
+            }
+            __syncwarp();
+            while (__any_sync(0xffffffffu, cnt != 0u)) step();
+            if (trace && lane == 0) {
+                for (int i = 0; i < 4; ++i) dbg_ts[(warp - 2) * 8 + i] = acc_t[i];
+                for (int i = 0; i < 3; ++i) dbg_ts[(warp - 2) * 8 + 4 + i] = stat[i];
+                dbg_ts[(warp - 2) * 8 + 7] = seq;
+                for (int i = 0; i < 7; ++i) dbg_ts[64 + (warp - 2) * 8 + i] = stat[3 + i];
+            }
+            // Output.  The register lists go to shared memory (over the record stacks, which are empty now); row r of this
+            // warp then merges the ascending lists of lanes r and r + 16: the 32 smallest of the 64 keys.
+            static_assert(2 * SL_KEEP >= 32 && SL_KEEP <= 32, "the merge below fills 32 output slots from two lists");
+            uint32_t* keys = reinterpret_cast<uint32_t*>(wbase + SL_ID_BYTES);   // [SL_KEEP entries][32 lanes]
+#pragma unroll
+            for (int i = 0; i < SL_KEEP; ++i) keys[i * 32 + lane] = l[i];
+            __syncwarp();
+            const uint32_t* idw = reinterpret_cast<const uint32_t*>(wbase);      // [32 slots][32 lanes]
+            const int64_t rowbase = (int64_t)m0 + row0;
+            const int64_t sbase = (int64_t)blockIdx.y * nq;
+#pragma unroll 1
+            for (int r = 0; r < 16; ++r) {
+                const int64_t row = rowbase + r;
+                if (row >= nq_eff) break;   // warp-uniform
+                // a ascending in lanes 0 .. SL_KEEP-1, b descending in lanes 32-SL_KEEP .. 31, ~0 elsewhere: bitonic split
+                const uint32_t ka = lane < SL_KEEP ? keys[lane * 32 + r] : 0xFFFFFFFFu;
+                const uint32_t kb = 31 - lane < SL_KEEP ? keys[(31 - lane) * 32 + r + 16] : 0xFFFFFFFFu;
+                const bool alo = ka <= kb;
+                const uint32_t lo = alo ? ka : kb, hi = alo ? kb : ka;
+                const uint32_t id = idw[(lo & SL_SLOT_MASK) * 32 + (alo ? r : r + 16)];
+                const uint32_t dropped = __reduce_min_sync(0xffffffffu, hi & ~SL_SLOT_MASK);     // lower bound of the dropped scores
+                const uint32_t ta = __shfl_sync(0xffffffffu, l[SL_KEEP - 1], r) & ~SL_SLOT_MASK;
+                const uint32_t tb = __shfl_sync(0xffffffffu, l[SL_KEEP - 1], r + 16) & ~SL_SLOT_MASK;
+                const int64_t o = (sbase + row) * KEEP + lane;
+                cand_idx[o] = (int32_t)id;                            // empty entries carry id -1
+                if (cand_score) cand_score[o] = ord_float(lo & ~SL_SLOT_MASK);
+                if (lane == 0) thr_out[sbase + row] = ord_float(min(min(ta, tb), dropped));
+            }
+            tc_fence_before();
+        } else {
         // Tiles arrive in the producer's order; entry seq of the tile-id ring names the tile in accumulator stage
         // seq % TS_STAGES (-1: end of the stream).  Quiet tiles (no score below any threshold of the warp's rows -- the
         // common case of a dense scan) stay a short dependent chain: wait, two TMEM loads, release, two min trees, ONE vote.
@@ -1190,6 +1400,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         }
         if (lane < 16 && rowbase + lane < nq_eff) thr_out[sbase + rowbase + lane] = thr;
         tc_fence_before();
+        }   // EPI == 0
     }
     __syncthreads();
     if (trace && threadIdx.x == 0) {
@@ -1687,14 +1898,15 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
     return 0;
 }
 
-static size_t ts_smem_bytes(int nslot, int E) {
-    return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * 16 * (32 * E) * 8 +
-           (size_t)TS_EPI_WARPS * 8 * 32 * 16 + (size_t)BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
+static size_t ts_smem_bytes(int nslot, int E, int epi = 0) {
+    const size_t lists = epi == 1 ? (size_t)TS_EPI_WARPS * SL_WARP_BYTES
+                                  : (size_t)TS_EPI_WARPS * 16 * (32 * E) * 8 + (size_t)TS_EPI_WARPS * 8 * 32 * 16;
+    return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + lists + (size_t)BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
            (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
 }
 // TS variant: the operand must fit the TMEM columns next to the accumulators and at least nbox+1 reference boxes must
 // fit in shared memory next to the candidate rows.
-static bool ts_variant_fits(int nbox, int E) { return nbox <= TS_MAX_NBOX && ts_smem_bytes(nbox + 1, E) <= (size_t)232448; }
+static bool ts_variant_fits(int nbox, int E, int epi = 0) { return nbox <= TS_MAX_NBOX && ts_smem_bytes(nbox + 1, E, epi) <= (size_t)232448; }
 
 static size_t candidates_smem_bytes(int nbox, int nslot, int E) {
     return 1024 /* alignment slack */ + (size_t)nbox * A_BOX_BYTES + (size_t)nslot * B_BOX_BYTES + (size_t)(4 * (32 * E + 32) * ROWPITCH + 2) * 8 + (size_t)4 * 8 * 32 * 16 +
@@ -1837,6 +2049,10 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     const bool ss_fits = candidates_smem_bytes(L.nbox, 3, E) <= (size_t)232448;
     const bool use_ts = ts_variant_fits(L.nbox, E) && !(ss_fits && kenv && strcmp(kenv, "ss") == 0);
     const int bn = use_ts ? TS_BN : BN;
+    // Epilogue of the TS kernel: per-thread heaps (lists of 32, the default) or the replace-the-maximum lists
+    // (lists of 64, B200MNN_EPI=0, or when the heaps do not fit next to the reference boxes).
+    const char* eenv = getenv("B200MNN_EPI");
+    const int epi = (use_ts && E == 1 && ts_variant_fits(L.nbox, E, 1) && !(eenv && atoi(eenv) == 0)) ? 1 : 0;
     // Pruned search (knn_cluster.cuh): reference rows grouped by a coarse k-means, query rows grouped by nearest centroid,
     // whole clusters skipped by a rigorous lower bound.  B200MNN_PRUNE=0 never, =1 whenever the shape allows, unset: for
     // searches large enough to pay for the clustering.  B200MNN_CLUSTERS sets the number of clusters (power of two).
@@ -1947,8 +2163,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         int nslot = MAX_SLOTS;
         size_t smem = 0;
         if (use_ts) {
-            while (nslot > nb + 1 && ts_smem_bytes(nslot, E) > (size_t)max_smem) --nslot;
-            smem = ts_smem_bytes(nslot, E);
+            while (nslot > nb + 1 && ts_smem_bytes(nslot, E, epi) > (size_t)max_smem) --nslot;
+            smem = ts_smem_bytes(nslot, E, epi);
         } else {
             while (nslot > 3 && candidates_smem_bytes(nb, nslot, E) > (size_t)max_smem) --nslot;
             smem = candidates_smem_bytes(nb, nslot, E);
@@ -1990,16 +2206,17 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         if (E == 1) B200_LAUNCH_CAND(1, NB); \
         else B200_LAUNCH_CAND(2, NB);        \
     } while (0)
-#define B200_LAUNCH_TS(EE, NB)                                                                                                   \
-    do {                                                                                                                          \
-        B200_CUDA(cudaFuncSetAttribute(knn_candidates_ts_kernel<EE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_ts_kernel<EE, NB>, opA_c, a_pitch, qmap, qcount, tmB, sch, nslot, nq_c,  \
-                                     ntiles, tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start, pargs));  \
+#define B200_LAUNCH_TS(EE, NB, EP)                                                                                                   \
+    do {                                                                                                                              \
+        B200_CUDA(cudaFuncSetAttribute(knn_candidates_ts_kernel<EE, NB, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, knn_candidates_ts_kernel<EE, NB, EP>, opA_c, a_pitch, qmap, qcount, tmB, sch, nslot, nq_c,  \
+                                     ntiles, tiles_per_split, cand_idx, cand_score, thr, dbg_mode, dbg_ts, trace_start, pargs));      \
     } while (0)
-#define B200_LAUNCH_TS_E(NB)               \
-    do {                                   \
-        if (E == 1) B200_LAUNCH_TS(1, NB); \
-        else B200_LAUNCH_TS(2, NB);        \
+#define B200_LAUNCH_TS_E(NB)                       \
+    do {                                           \
+        if (epi == 1) B200_LAUNCH_TS(1, NB, 1);    \
+        else if (E == 1) B200_LAUNCH_TS(1, NB, 0); \
+        else B200_LAUNCH_TS(2, NB, 0);             \
     } while (0)
         if (use_ts) {
             switch (nb) {

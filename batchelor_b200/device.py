@@ -176,17 +176,60 @@ def _two_side_streams(device):
     return _side_streams[key]
 
 
+def direction_split(n1: int, n2: int, world: int, rank: int) -> Tuple[int, int, int, int, int]:
+    """Work split of findMutualNN over `world` >= 2 ranks: the first h ranks search (contiguous blocks of) the batch-1
+    rows in batch 2, the other world - h ranks the batch-2 rows in batch 1, h proportional to n1 : n2.  Every rank then
+    builds the reference-side plan of ONE direction only (with both directions on every rank that plan -- k-means,
+    grouping, operand preparation: work that does not shrink with the shard -- is paid twice per rank).
+    Returns (direction, lo, hi, rows_per_rank_of_that_direction, h)."""
+    h = min(world - 1, max(1, int(round(world * n1 / max(1, n1 + n2)))))
+    if rank < h:
+        lo, hi, per = shard_bounds(n1, h, rank)
+        return 0, lo, hi, per, h
+    lo, hi, per = shard_bounds(n2, world - h, rank - h)
+    return 1, lo, hi, per, h
+
+
+def direction_split_gather(local: torch.Tensor, n1: int, k2: int, n2: int, k1: int, world: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exchange step of :func:`direction_split` (backend-agnostic like :func:`all_gather_rows`): `local` is this rank's
+    block of neighbour indices ([rows, k2] on the first h ranks, [rows, k1] on the others).  One all-gather of equally
+    padded blocks; returns (w21 [n1, k2], w12 [n2, k1]) on every rank."""
+    import torch.distributed as dist_
+
+    h = direction_split(n1, n2, world, 0)[4]
+    per1 = (n1 + h - 1) // h
+    per2 = (n2 + (world - h) - 1) // (world - h)
+    per, kmax = max(per1, per2), max(k1, k2)
+    pad = torch.zeros((per, kmax), dtype=torch.int32, device=local.device)
+    pad[: local.shape[0], : local.shape[1]] = local
+    full = torch.empty((world, per, kmax), dtype=torch.int32, device=local.device)
+    dist_.all_gather_into_tensor(full.view(world * per, kmax), pad)
+    w21 = full[:h, :per1, :k2].reshape(h * per1, k2)[:n1].contiguous()
+    w12 = full[h:, :per2, :k1].reshape((world - h) * per2, k1)[:n2].contiguous()
+    return w21, w12
+
+
 def find_mutual_nn(data1: torch.Tensor, data2: torch.Tensor, k1: int, k2: int, sharded: bool = True):
     """findMutualNN(data1, data2, k1, k2): two exact searches + mutual pairs.  Returns (first, second, w21, w12).
 
     The two searches are independent, so their kernels are enqueued on two side streams: the serial stretches of one
     direction's cluster plan (a one-block seeding kernel, small scans) overlap with the other direction's work.  With a
-    process group the local shards are computed that way and the two all-gathers follow on the caller's stream."""
+    process group the ranks split the DIRECTIONS first and the query rows second (:func:`direction_split`), and one
+    all-gather of the index blocks follows on the caller's stream."""
     import torch.distributed as dist_
 
     k1 = min(k1, data1.shape[0]); k2 = min(k2, data2.shape[0])
     n1, n2 = data1.shape[0], data2.shape[0]
     ws = dist_.get_world_size() if (sharded and dist_.is_available() and dist_.is_initialized()) else 1
+    if ws > 1 and min(n1, n2) >= ws * 2048:
+        direction, lo, hi, _, _ = direction_split(n1, n2, ws, dist_.get_rank())
+        if direction == 0:
+            mine, _ = query_knn(data2, data1[lo:hi], k2, want_dist=False)   # neighbours of batch-1 cells in batch 2
+        else:
+            mine, _ = query_knn(data1, data2[lo:hi], k1, want_dist=False)   # neighbours of batch-2 cells in batch 1
+        w21, w12 = direction_split_gather(mine, n1, k2, n2, k1, ws)
+        first, second = find_mutual_nns(w21, w12)
+        return first, second, w21, w12
     split1 = ws > 1 and n1 >= ws * 2048     # batch-1 cells are the queries of the first search
     split2 = ws > 1 and n2 >= ws * 2048
     rank = dist_.get_rank() if ws > 1 else 0
