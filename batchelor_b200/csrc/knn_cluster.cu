@@ -302,38 +302,26 @@ __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __r
                                                              const double* __restrict__ cinv, unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
                                                              const double* __restrict__ qnorm, const int* __restrict__ scale_exp,
                                                              int2* __restrict__ lists, float* __restrict__ qoff) {
-    extern __shared__ double rows[];                 // [128][dp] rows, then [d][C] transposed centroids
-    double* cenT = rows + CL_TILE * dp;
+    // Shared memory holds the transposed centroids only: every thread reads its (gathered) row straight from global
+    // memory -- 400 contiguous bytes that stay in L1 across the passes -- so eight blocks fit an SM instead of two
+    // (staging the 128 rows took 52 KB per block and left the kernel latency-bound at 8 warps per SM).
+    extern __shared__ double cenT[];                 // [d][C] transposed centroids
     __shared__ unsigned long long red[CL_MAXC];
     __shared__ int src_s[CL_TILE];
+    (void)dp;
     const int64_t row0 = (int64_t)blockIdx.x * CL_TILE;
     if (count && row0 >= (int64_t)*count) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     src_s[tid] = (!count || row0 + tid < (int64_t)*count) ? map[row0 + tid] : -1;
     for (int c = tid; c < CL_MAXC; c += CL_TILE) red[c] = (MODE == 0) ? dkey(-INFINITY) : dkey(INFINITY);
     __syncthreads();
     if (MODE == 0 && src_s[0] < 0) return;           // clusters are padded at their end: an empty first row = an unused tile
-    for (int t0 = 0; t0 < d; t0 += 32) {   // gathered rows: eight independent loads in flight per lane
-        const int t = t0 + lane;
-#pragma unroll 1
-        for (int rb = warp * 32; rb < warp * 32 + 32; rb += 8) {
-            double v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t s = src_s[rb + u];
-                v[u] = (s >= 0 && t < d) ? X[s * d + t] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (t < d) rows[(rb + u) * dp + t] = v[u];
-        }
-    }
     load_centroids_t(cen, C, d, cenT);
     __syncthreads();
     const int src = src_s[tid];
     const bool valid = src >= 0;
     const int P = valid ? cid[src] : 0;
-    const double* x = rows + tid * dp;
+    const double* x = X + (int64_t)(valid ? src : src_s[0] < 0 ? 0 : src_s[0]) * d;   // padding rows read a valid row; their values are discarded
     const double M = sqrt(__longlong_as_double((long long)*maxnorm_bits));
     double gP = 0.0, xn = 0.0;
     for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, cenT[t * C + P], gP); xn = fma(xv, xv, xn); }
@@ -509,10 +497,10 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     B200_TRY(set_smem((const void*)lloyd_accum_kernel, row_smem));
     B200_TRY(set_smem((const void*)assign_kernel<16>, cen_smem));
     B200_TRY(set_smem((const void*)assign_kernel<64>, cen_smem));
-    B200_TRY(set_smem((const void*)tile_project_kernel<0, 16>, row_smem));
-    B200_TRY(set_smem((const void*)tile_project_kernel<1, 16>, row_smem));
-    B200_TRY(set_smem((const void*)tile_project_kernel<0, 64>, row_smem));
-    B200_TRY(set_smem((const void*)tile_project_kernel<1, 64>, row_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<0, 16>, cen_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<1, 16>, cen_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<0, 64>, cen_smem));
+    B200_TRY(set_smem((const void*)tile_project_kernel<1, 64>, cen_smem));
 
     gather_sample_kernel<<<(unsigned)ceil_div((int64_t)m * d, 256), 256, 0, stream>>>(dX, n, d, m, sample);
     B200_LAUNCH_CHECK();
@@ -558,10 +546,10 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     fill_vref_kernel<<<(unsigned)ceil_div((int64_t)C * C, 256), 256, 0, stream>>>(p.vref, C * C);
     B200_LAUNCH_CHECK();
     if (C % 64 == 0)
-        tile_project_kernel<0, 64><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
+        tile_project_kernel<0, 64><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, cen_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
                                                                                                 p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
     else
-        tile_project_kernel<0, 16><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, row_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
+        tile_project_kernel<0, 16><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, cen_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
                                                                                                 p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
     B200_TRY(build_tile_lists(p, dQ, d, p.qmap, p.nslots, p.nslots_max, qnorm, scale_exp, maxnorm_bits, p.cl_list, p.qoff, stream));
@@ -586,7 +574,7 @@ int build_tile_lists(const ClusterPlan& p, const double* dQ, int d, const int32_
                      const double* qnorm, const int* scale_exp, const unsigned long long* maxnorm_bits, int2* lists, float* qoff,
                      cudaStream_t stream) {
     const int dp = d | 1;
-    const size_t row_smem = ((size_t)CL_TILE * dp + (size_t)p.C * d) * sizeof(double);
+    const size_t row_smem = (size_t)p.C * d * sizeof(double);   // transposed centroids
     if (p.C % 64 == 0)
         tile_project_kernel<1, 64><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids_t, p.cdist,
                                                                                              p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);

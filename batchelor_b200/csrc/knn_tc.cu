@@ -1256,6 +1256,9 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                 ++seq;
                 if (trace) { c2 = clock64(); acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; }
                 if (dbg_mode == 1) continue;
+                // Dense scan (no cluster plan): most tiles hold no score below any threshold of the warp -- two min trees and
+                // one vote skip them.  (With pruning nearly every tile is one of the queries' own component and has hits.)
+                if (P.cl_list == nullptr && !__any_sync(0xffffffffu, fminf(chunk_min(v0), chunk_min(v1)) < thr)) continue;
                 const uint32_t idb = (uint32_t)tile * (uint32_t)TS_BN + (uint32_t)(lane >> 4) * 32u;   // reference of v0[0]; v1[0] is 64 further
                 // ONE copy of the step code (the loop is not unrolled); 32 scores = 8 quads need room for 8 records
 #pragma unroll 1
