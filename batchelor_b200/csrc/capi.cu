@@ -152,6 +152,41 @@ int b200mnn_query_knn(const double* X, int64_t n, const double* Q, int64_t nq, i
     return finish(s, nullptr, "");
 }
 
+// Host buffers -> device, pipelined (large row counts): batch 1 crosses PCIe first; while batch 2 follows in row chunks,
+// the GPU already prepares batch 1 as the reference set of the second search (norms, cluster plan, grouped operand) and
+// then answers every chunk of batch-2 rows as soon as it has landed (knn::RefCache).  The first search (batch-1 rows in
+// batch 2) needs all of batch 2 and starts when the last chunk is in.  Results are identical to the unpipelined order of
+// operations: every search is exact.
+static const int64_t kPipelineMinRows = 262144;
+static const int kPipelineChunks = 3;   // measured at 1M x 1M x 50: 2-3 chunks 55.9 ms, 4: 56.4, 6: 57.5, unpipelined 61.5
+
+struct EventPool {   // events of one call, destroyed at scope exit
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    cudaEvent_t make() {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ev.push_back(e);
+        return e;
+    }
+};
+
+// Uploads rows [r0, r1) of a host [rows x cols] matrix (column-major: R layout; else row-major) into the row-major device
+// matrix `dst` ([rows x cols]); `raw` is a device staging buffer of (r1 - r0) * cols doubles for the column-major case.
+static int upload_rows(const double* host, int64_t rows, int64_t cols, bool col_major, int64_t r0, int64_t r1, double* dst, double* raw,
+                       cudaStream_t s) {
+    const int64_t nr = r1 - r0;
+    if (nr <= 0) return 0;
+    if (!col_major || cols <= 1) {
+        B200_CUDA(cudaMemcpyAsync(dst + r0 * cols, host + r0 * cols, sizeof(double) * (size_t)nr * cols, cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    // column t of the chunk: host[t * rows + r0 ...] -> raw[t * nr ...] (a column-major [nr x cols] block), then transpose
+    B200_CUDA(cudaMemcpy2DAsync(raw, sizeof(double) * (size_t)nr, host + r0, sizeof(double) * (size_t)rows, sizeof(double) * (size_t)nr, (size_t)cols,
+                                cudaMemcpyHostToDevice, s));
+    return correct::transpose_device<double>(raw, nr, cols, dst + r0 * cols, s);
+}
+
 int b200mnn_find_mutual_nn(const double* data1, int64_t n1, const double* data2, int64_t n2, int d, int k1, int k2, int col_major,
                            int32_t* first_out, int32_t* second_out, int64_t capacity, int64_t* np_out) {
     B200_TRY(ensure_device());
@@ -163,11 +198,19 @@ int b200mnn_find_mutual_nn(const double* data1, int64_t n1, const double* data2,
     if (n1 == 0 || n2 == 0 || k1 == 0 || k2 == 0) return 0;
     cudaStream_t s = lib_stream();
     Scratch ws(s);
+    SideStreams* ss = getenv("B200MNN_SERIAL") ? nullptr : side_streams();   // B200MNN_SERIAL: both searches on the one stream
+    int64_t min_rows = kPipelineMinRows;
+    if (const char* e = getenv("B200MNN_PIPELINE_MIN_ROWS")) min_rows = std::max<int64_t>(256, atoll(e));   // tests exercise the path on small inputs
+    const bool pipelined = ss && !getenv("B200MNN_NO_PIPELINE") && n1 >= min_rows && n2 >= min_rows && d > 0 &&
+                           knn::tensor_path_supported(n1, n2 / kPipelineChunks, d, k1);
     int rc;
     double* d1 = stage_matrix(ws, data1, n1, d, col_major != 0, s, &rc);
     if (rc) return rc;
-    double* d2 = stage_matrix(ws, data2, n2, d, col_major != 0, s, &rc);
-    if (rc) return rc;
+    double* d2 = nullptr;
+    if (!pipelined) {
+        d2 = stage_matrix(ws, data2, n2, d, col_major != 0, s, &rc);
+        if (rc) return rc;
+    }
     int32_t* w21 = ws.get<int32_t>((size_t)n1 * k2);  // neighbours of batch-1 cells in batch 2
     int32_t* w12 = ws.get<int32_t>((size_t)n2 * k1);  // neighbours of batch-2 cells in batch 1
     const int64_t cap = std::min<int64_t>(capacity, n1 * (int64_t)k2);
@@ -175,7 +218,62 @@ int b200mnn_find_mutual_nn(const double* data1, int64_t n1, const double* data2,
     int32_t* dsecond = ws.get<int32_t>((size_t)std::max<int64_t>(cap, 1));
     int64_t* dnp = ws.get<int64_t>(1);
     if (!ws.ok()) return B200MNN_ENOMEM;
-    SideStreams* ss = getenv("B200MNN_SERIAL") ? nullptr : side_streams();   // B200MNN_SERIAL: both searches on the one stream
+    EventPool events;
+    if (pipelined) {
+        knn::RefCache cache(ss->a);   // batch 1 as the reference set of the second search; lives on stream a
+        int nchunks = kPipelineChunks;
+        if (const char* e = getenv("B200MNN_PIPELINE_CHUNKS")) nchunks = std::max(1, std::min(64, atoi(e)));
+        const int64_t chunk = round_up(ceil_div(n2, nchunks), 128);
+        const bool cm = col_major != 0 && d > 1;
+        d2 = ws.get<double>((size_t)n2 * d);
+        double* raw = cm ? ws.get<double>((size_t)chunk * d) : nullptr;
+        if (!ws.ok()) return B200MNN_ENOMEM;
+        auto bail = [&](int code) {   // the scratch buffers must outlive whatever was enqueued on the side streams
+            const std::string msg = b200mnn_last_error();
+            cudaDeviceSynchronize();
+            cudaGetLastError();
+            return fail(code, msg);
+        };
+        cudaEvent_t e1 = events.make();
+        if (!e1) return fail(B200MNN_ECUDA, "cudaEventCreate failed");
+        B200_CUDA(cudaEventRecord(e1, s));                 // batch 1 (and every buffer allocated above) is ready
+        B200_CUDA(cudaStreamWaitEvent(ss->a, e1, 0));
+        cache.nq_hint = std::min(chunk, n2);
+        rc = knn::query_knn_device(d1, n1, nullptr, 0, d, k1, nullptr, nullptr, nullptr, ss->a, nullptr, &cache);   // reference side only
+        if (rc) return bail(rc);
+        for (int64_t r0 = 0; r0 < n2; r0 += chunk) {
+            const int64_t r1 = std::min(n2, r0 + chunk);
+            rc = upload_rows(data2, n2, d, cm, r0, r1, d2, raw, s);
+            if (rc) return bail(rc);
+            cudaEvent_t ec = events.make();
+            if (!ec) return bail(B200MNN_ECUDA);
+            if (cudaEventRecord(ec, s) != cudaSuccess || cudaStreamWaitEvent(ss->a, ec, 0) != cudaSuccess) return bail(B200MNN_ECUDA);
+            // (copies and transposes share stream s: the next chunk's copy into `raw` is ordered after this chunk's transpose)
+            rc = knn::query_knn_device(d1, n1, d2 + r0 * d, r1 - r0, d, k1, w12 + r0 * k1, nullptr, nullptr, ss->a, nullptr, &cache);
+            if (rc) return bail(rc);
+        }
+        cudaEvent_t e2 = events.make();
+        if (!e2) return bail(B200MNN_ECUDA);
+        if (cudaEventRecord(e2, s) != cudaSuccess || cudaStreamWaitEvent(ss->b, e2, 0) != cudaSuccess) return bail(B200MNN_ECUDA);
+        rc = knn::query_knn_device(d2, n2, d1, n1, d, k2, w21, nullptr, nullptr, ss->b, nullptr);
+        if (rc) return bail(rc);
+        if (cudaEventRecord(ss->done_a, ss->a) != cudaSuccess || cudaEventRecord(ss->done_b, ss->b) != cudaSuccess ||
+            cudaStreamWaitEvent(s, ss->done_a, 0) != cudaSuccess || cudaStreamWaitEvent(s, ss->done_b, 0) != cudaSuccess)
+            return bail(B200MNN_ECUDA);
+        rc = mutual::find_mutual_nns_device(w21, n1, k2, w12, n2, k1, dfirst, dsecond, cap, dnp, 1, nullptr, s);
+        if (rc) return bail(rc);
+        int64_t np = 0;
+        if (cudaMemcpyAsync(&np, dnp, sizeof(int64_t), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+            return bail(B200MNN_ECUDA);
+        // everything on the side streams is complete here: the cache may release its buffers at scope exit
+        *np_out = np;
+        if (np > capacity) return fail(B200MNN_ECAPACITY, "pair output capacity too small");
+        if (np > 0) {
+            B200_CUDA(cudaMemcpyAsync(first_out, dfirst, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, s));
+            B200_CUDA(cudaMemcpyAsync(second_out, dsecond, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, s));
+        }
+        return finish(s, nullptr, "");
+    }
     if (ss) {
         B200_CUDA(cudaEventRecord(ss->start, s));
         B200_CUDA(cudaStreamWaitEvent(ss->a, ss->start, 0));

@@ -3,14 +3,36 @@
 #pragma once
 
 #include "common.cuh"
+#include "knn_cluster.cuh"
 
 namespace b200 {
 
 namespace knn {
 struct DebugOut;
 bool tensor_path_supported(int64_t n, int64_t nq, int d, int k);
+// Reference side of a search -- row norms, the scale, the cluster plan, the grouped fp16 operand -- kept so that several
+// calls can search the same reference set (b200mnn_find_mutual_nn searches batch 2 chunk by chunk against batch 1 while
+// batch 2 is still crossing PCIe).  The first call with a cache fills it (nq == 0: that and nothing else); later calls must pass
+// the same dX / n / d / k and
+// run on the cache's stream.  With a cache the fp16 scale is derived from the reference rows alone (a query row more than
+// 4x larger than every reference coordinate overflows fp16, fails its certificate and is answered by the exact rescue
+// scan: slower, never wrong).
+struct RefCache {
+    explicit RefCache(cudaStream_t s) : ws(s) {}
+    Scratch ws;              // owns the reference-side buffers
+    bool ready = false;
+    const double* dX = nullptr;
+    int64_t n = 0;
+    int d = 0, k = 0;
+    bool use_prune = false;
+    int64_t nq_hint = 0;     // query rows per search expected by a prepare-only call (nq == 0)
+    void* opB = nullptr;
+    double* xnorm = nullptr;
+    unsigned char* scalars = nullptr;   // absmax_bits, scale_exp, maxnorm_bits, bmax_bits
+    ClusterPlan plan;        // reference part
+};
 int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
-                     int64_t* d_stats, cudaStream_t stream, const DebugOut* dbg);
+                     int64_t* d_stats, cudaStream_t stream, const DebugOut* dbg, RefCache* cache = nullptr);
 // knn_wide.cu: K-streamed tensor-core path for wide data / large k
 bool wide_path_supported(int64_t n, int64_t nq, int d, int k);
 int query_knn_wide(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,

@@ -243,18 +243,8 @@ __global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restric
     if (valid && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + c, __popc(peers));
 }
 
-// tile0[c]: first reference tile of cluster c; slot_base[c]: first query slot of cluster c; cursors zeroed.  Query
-// slots are laid out by DESCENDING reference count of their cluster: a query tile's work is roughly the size of its own
-// cluster, and starting the heavy CTAs first shortens the tail of the scoring kernel.
-__global__ void offsets_kernel(const int* __restrict__ cnt_ref, const int* __restrict__ cnt_q, int C, int* __restrict__ tile0,
-                               int* __restrict__ row_base, int* __restrict__ slot_base, int* __restrict__ nslots, int* __restrict__ cursors) {
-    __shared__ int order[CL_MAXC];
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // rank of cluster c by (reference count descending, id ascending)
-        int rank = 0;
-        for (int o = 0; o < C; ++o) rank += (cnt_ref[o] > cnt_ref[c] || (cnt_ref[o] == cnt_ref[c] && o < c)) ? 1 : 0;
-        order[rank] = c;
-    }
-    __syncthreads();
+// Reference side: tile0[c] = first reference tile of cluster c, row_base[c] = its first grouped row.
+__global__ void ref_offsets_kernel(const int* __restrict__ cnt_ref, int C, int* __restrict__ tile0, int* __restrict__ row_base) {
     if (threadIdx.x == 0) {
         int t = 0;
         for (int c = 0; c < C; ++c) {
@@ -263,6 +253,21 @@ __global__ void offsets_kernel(const int* __restrict__ cnt_ref, const int* __res
             t += (cnt_ref[c] + CL_TILE - 1) / CL_TILE;
         }
         tile0[C] = t;
+    }
+}
+// Query side: slot_base[c] = first query slot of cluster c.  Query slots are laid out by DESCENDING reference count of
+// their cluster: a query tile's work is roughly the size of its own cluster, and starting the heavy CTAs first shortens
+// the tail of the scoring kernel.
+__global__ void query_offsets_kernel(const int* __restrict__ cnt_ref, const int* __restrict__ cnt_q, int C, int* __restrict__ slot_base,
+                                     int* __restrict__ nslots) {
+    __shared__ int order[CL_MAXC];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {   // rank of cluster c by (reference count descending, id ascending)
+        int rank = 0;
+        for (int o = 0; o < C; ++o) rank += (cnt_ref[o] > cnt_ref[c] || (cnt_ref[o] == cnt_ref[c] && o < c)) ? 1 : 0;
+        order[rank] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         int s = 0;
         for (int i = 0; i < C; ++i) {
             const int c = order[i];
@@ -271,7 +276,6 @@ __global__ void offsets_kernel(const int* __restrict__ cnt_ref, const int* __res
         }
         *nslots = s;
     }
-    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) cursors[c] = 0;
 }
 
 __global__ void scatter_kernel(const int32_t* __restrict__ cid, int64_t n, const int* __restrict__ base, int* __restrict__ cursor,
@@ -448,50 +452,41 @@ static int set_smem(const void* fn, size_t bytes) {
     return 0;
 }
 
-int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int C, const double* qnorm, const int* scale_exp,
-                       const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream, ClusterPlan* plan) {
+int build_ref_plan(const double* dX, int64_t n, int d, int C, const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream,
+                   ClusterPlan* plan) {
     if (C < 16 || C > CL_MAXC || (C & (C - 1)) != 0) return fail(B200MNN_EINVAL, "internal: cluster count must be a power of two in [16, 256]");
     int m = (int)std::min<int64_t>(n, SAMPLE_MAX);
     const int mf = std::min(m, FPS_MAX);
     m = (m / mf) * mf;          // the seeding walks the sample with an integer stride
     if (mf < C) return fail(B200MNN_EINVAL, "internal: too few rows for the requested number of clusters");
     const int dp = d | 1;
-    const size_t row_smem = ((size_t)CL_TILE * dp + (size_t)C * d) * sizeof(double);   // staged rows + transposed centroids
+    const size_t row_smem = ((size_t)CL_TILE * dp + (size_t)C * d) * sizeof(double);   // staged rows + transposed centroids (Lloyd steps)
     if (row_smem > (size_t)200 * 1024) return fail(B200MNN_EINVAL, "internal: too many dimensions for the cluster plan");
 
     ClusterPlan& p = *plan;
     p.C = C;
     p.n_rows_max = round_up(n, CL_TILE) + (int64_t)C * CL_TILE;
-    p.nslots_max = round_up(nq, CL_TILE) + (int64_t)C * CL_TILE;
     p.refmap = ws.get<int32_t>((size_t)p.n_rows_max);
-    p.qmap = ws.get<int32_t>((size_t)p.nslots_max);
-    p.cl_list = ws.get<int2>((size_t)(p.nslots_max / CL_TILE) * C);
-    p.qoff = ws.get<float>((size_t)p.nslots_max);
-    p.cid_q = ws.get<int32_t>((size_t)nq);
     p.centroids = ws.get<double>((size_t)C * d);
     p.cdist = ws.get<double>((size_t)C * C);
     p.cinv = ws.get<double>((size_t)C * C);
     p.centroids_t = ws.get<double>((size_t)C * d);
     p.vref = ws.get<unsigned long long>((size_t)C * C);
+    p.cnorm = ws.get<double>((size_t)C);
     int32_t* cid_ref = ws.get<int32_t>((size_t)n);
     double* sample = ws.get<double>((size_t)m * d);
     double* subset_t = ws.get<double>((size_t)mf * d);
     double* sums = ws.get<double>((size_t)C * d);
-    double* cnorm = ws.get<double>((size_t)C);
-    int* ints = ws.get<int>((size_t)8 * CL_MAXC + 16);
+    int* ints = ws.get<int>((size_t)5 * CL_MAXC + 16);
     if (!ws.ok()) return B200MNN_ENOMEM;
     int* counts = ints;                    // [C]   Lloyd counts
-    int* cnt_ref = ints + CL_MAXC;         // [C]
-    int* cnt_q = ints + 2 * CL_MAXC;       // [C]
-    int* row_base = ints + 3 * CL_MAXC;    // [C]
-    int* slot_base = ints + 4 * CL_MAXC;   // [C]
-    int* cursors = ints + 5 * CL_MAXC;     // [2C]
-    p.cl_tile0 = ints + 7 * CL_MAXC;       // [C + 1]
-    p.nslots = ints + 8 * CL_MAXC + 8;
-    B200_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * (8 * CL_MAXC + 16), stream));
+    p.cnt_ref = ints + CL_MAXC;            // [C]
+    int* row_base = ints + 2 * CL_MAXC;    // [C]
+    int* cursors = ints + 3 * CL_MAXC;     // [C]
+    p.cl_tile0 = ints + 4 * CL_MAXC;       // [C + 1]
+    B200_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * (5 * CL_MAXC + 16), stream));
     B200_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * (size_t)C * d, stream));
     B200_CUDA(cudaMemsetAsync(p.refmap, 0xFF, sizeof(int32_t) * (size_t)p.n_rows_max, stream));
-    B200_CUDA(cudaMemsetAsync(p.qmap, 0xFF, sizeof(int32_t) * (size_t)p.nslots_max, stream));
 
     const size_t cen_smem = (size_t)C * d * sizeof(double);
     B200_TRY(set_smem((const void*)lloyd_accum_kernel, row_smem));
@@ -509,38 +504,28 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     fps_seed_kernel<<<1, 1024, (size_t)d * sizeof(double), stream>>>(subset_t, d, mf, C, p.centroids);
     B200_LAUNCH_CHECK();
     for (int it = 0; it < LLOYD_ITERS; ++it) {
-        centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
+        centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, p.cnorm);
         B200_LAUNCH_CHECK();
         transpose_centroids_kernel<<<(unsigned)ceil_div((int64_t)C * d, 256), 256, 0, stream>>>(p.centroids, C, d, p.centroids_t);
         B200_LAUNCH_CHECK();
-        lloyd_accum_kernel<<<(unsigned)ceil_div(m, CL_TILE), CL_TILE, row_smem, stream>>>(sample, m, d, dp, C, p.centroids_t, cnorm, sums, counts);
+        lloyd_accum_kernel<<<(unsigned)ceil_div(m, CL_TILE), CL_TILE, row_smem, stream>>>(sample, m, d, dp, C, p.centroids_t, p.cnorm, sums, counts);
         B200_LAUNCH_CHECK();
         lloyd_update_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, sums, counts);
         B200_LAUNCH_CHECK();
     }
-    centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, cnorm);
+    centroid_norm_kernel<<<1, CL_MAXC, 0, stream>>>(p.centroids, C, d, p.cnorm);
     B200_LAUNCH_CHECK();
     centroid_dist_kernel<<<C, 64, 0, stream>>>(p.centroids, C, d, p.cdist, p.cinv);
     B200_LAUNCH_CHECK();
     transpose_centroids_kernel<<<(unsigned)ceil_div((int64_t)C * d, 256), 256, 0, stream>>>(p.centroids, C, d, p.centroids_t);
     B200_LAUNCH_CHECK();
 
-    if (C % 64 == 0) {
-        assign_kernel<64><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, cnorm, cid_ref, cnt_ref);
-        B200_LAUNCH_CHECK();
-        assign_kernel<64><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, cnorm, p.cid_q, cnt_q);
-        B200_LAUNCH_CHECK();
-    } else {
-        assign_kernel<16><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, cnorm, cid_ref, cnt_ref);
-        B200_LAUNCH_CHECK();
-        assign_kernel<16><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, cnorm, p.cid_q, cnt_q);
-        B200_LAUNCH_CHECK();
-    }
-    offsets_kernel<<<1, 256, 0, stream>>>(cnt_ref, cnt_q, C, p.cl_tile0, row_base, slot_base, p.nslots, cursors);
+    if (C % 64 == 0) assign_kernel<64><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, p.cnorm, cid_ref, p.cnt_ref);
+    else assign_kernel<16><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, p.cnorm, cid_ref, p.cnt_ref);
+    B200_LAUNCH_CHECK();
+    ref_offsets_kernel<<<1, 32, 0, stream>>>(p.cnt_ref, C, p.cl_tile0, row_base);
     B200_LAUNCH_CHECK();
     scatter_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(cid_ref, n, row_base, cursors, p.refmap);
-    B200_LAUNCH_CHECK();
-    scatter_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, stream>>>(p.cid_q, nq, slot_base, cursors + C, p.qmap);
     B200_LAUNCH_CHECK();
 
     fill_vref_kernel<<<(unsigned)ceil_div((int64_t)C * C, 256), 256, 0, stream>>>(p.vref, C * C);
@@ -551,6 +536,34 @@ int build_cluster_plan(const double* dX, int64_t n, const double* dQ, int64_t nq
     else
         tile_project_kernel<0, 16><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, cen_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
                                                                                                 p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int build_query_plan(ClusterPlan* plan, const double* dQ, int64_t nq, int d, const double* qnorm, const int* scale_exp,
+                     const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream) {
+    ClusterPlan& p = *plan;
+    const int C = p.C;
+    p.nslots_max = round_up(nq, CL_TILE) + (int64_t)C * CL_TILE;
+    p.qmap = ws.get<int32_t>((size_t)p.nslots_max);
+    p.cl_list = ws.get<int2>((size_t)(p.nslots_max / CL_TILE) * C);
+    p.qoff = ws.get<float>((size_t)p.nslots_max);
+    p.cid_q = ws.get<int32_t>((size_t)nq);
+    int* ints = ws.get<int>((size_t)3 * CL_MAXC + 16);
+    if (!ws.ok()) return B200MNN_ENOMEM;
+    int* cnt_q = ints;                     // [C]
+    int* slot_base = ints + CL_MAXC;       // [C]
+    int* cursors = ints + 2 * CL_MAXC;     // [C]
+    p.nslots = ints + 3 * CL_MAXC + 8;
+    B200_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * (3 * CL_MAXC + 16), stream));
+    B200_CUDA(cudaMemsetAsync(p.qmap, 0xFF, sizeof(int32_t) * (size_t)p.nslots_max, stream));
+    const size_t cen_smem = (size_t)C * d * sizeof(double);
+    if (C % 64 == 0) assign_kernel<64><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, p.cnorm, p.cid_q, cnt_q);
+    else assign_kernel<16><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, p.cnorm, p.cid_q, cnt_q);
+    B200_LAUNCH_CHECK();
+    query_offsets_kernel<<<1, 256, 0, stream>>>(p.cnt_ref, cnt_q, C, slot_base, p.nslots);
+    B200_LAUNCH_CHECK();
+    scatter_kernel<<<(unsigned)ceil_div(nq, 256), 256, 0, stream>>>(p.cid_q, nq, slot_base, cursors, p.qmap);
     B200_LAUNCH_CHECK();
     B200_TRY(build_tile_lists(p, dQ, d, p.qmap, p.nslots, p.nslots_max, qnorm, scale_exp, maxnorm_bits, p.cl_list, p.qoff, stream));
     return 0;

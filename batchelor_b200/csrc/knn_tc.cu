@@ -2024,15 +2024,21 @@ int write_stats(const int* flag_count, int64_t* d_stats, int64_t lists, int64_t 
 }
 
 int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, int d, int k, int32_t* d_idx, double* d_dist,
-                     int64_t* d_stats, cudaStream_t stream, const DebugOut* dbg) {
+                     int64_t* d_stats, cudaStream_t stream, const DebugOut* dbg, RefCache* cache) {
     B200_TRY(ensure_device());
     if (n < 0 || nq < 0 || d < 0) return fail(B200MNN_EINVAL, "negative dimension");
     if (k < 0 || k > n) return fail(B200MNN_EINVAL, "'k' must be positive and no larger than the number of points in 'X'");
-    if (nq == 0 || k == 0) return 0;
+    if ((nq == 0 && !cache) || k == 0) return 0;   // with a cache, nq == 0 prepares the reference side only
     if (n > (int64_t)INT32_MAX - 512 || nq > (int64_t)INT32_MAX - 512) return fail(B200MNN_EINVAL, "more than 2^31 points are not supported");
     Scratch ws(stream);
+    const bool ref_ready = cache && cache->ready;
+    if (nq == 0 && ref_ready) return 0;
+    if (ref_ready && (cache->dX != dX || cache->n != n || cache->d != d || cache->k != k))
+        return fail(B200MNN_EINVAL, "internal: reference cache used with a different reference set");
+    Scratch& rws = cache ? cache->ws : ws;   // owner of the reference-side buffers
 
-    if (!tensor_path_supported(n, nq, d, k) || d == 0) {
+    if (!tensor_path_supported(n, std::max<int64_t>(nq, 1), d, k) || d == 0) {
+        if (nq == 0) return 0;   // nothing to prepare outside the tensor path
         if (dbg) return fail(B200MNN_EINVAL, "debug candidates requested for a shape outside the tensor path");
         // wide rows (gene space) or large k: K-streamed tensor-core scoring + selection (knn_wide.cu); B200MNN_WIDE=0 forces
         // the generic exact scan, which is also what remains for k beyond the candidate capacity
@@ -2066,21 +2072,64 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     }
     const char* penv = getenv("B200MNN_PRUNE");
     const bool prune_ok = use_ts && !dbg && n >= 8 * (int64_t)nclusters && ((size_t)CL_TILE * (d | 1) + (size_t)nclusters * d) * sizeof(double) <= (size_t)200 * 1024;
-    const bool use_prune = prune_ok && (penv ? atoi(penv) == 1 : (n >= 65536 && nq >= 16384));
+    const int64_t nq_plan = (cache && nq == 0) ? cache->nq_hint : nq;   // rows a prepare-only call expects per search
+    const bool use_prune = ref_ready ? cache->use_prune : (prune_ok && (penv ? atoi(penv) == 1 : (n >= 65536 && nq_plan >= 16384)));
     const int64_t n_pad = use_prune ? round_up(n, CL_TILE) + (int64_t)nclusters * CL_TILE : round_up(n, bn);
     const int64_t nq_pad = round_up(nq, BM);
     const int64_t nslots = use_prune ? round_up(nq, CL_TILE) + (int64_t)nclusters * CL_TILE : nq;   // rows of the candidate / threshold arrays
     const int ntiles = (int)(n_pad / bn);
     const int mtiles = use_prune ? (int)(nslots / BM) : (int)(nq_pad / BM);
     int nsplit = 1;
-    if (!use_prune && mtiles < 2 * sm_count()) nsplit = (int)std::min<int64_t>(std::min<int64_t>(MAX_SPLIT, ntiles), ceil_div(2 * sm_count(), mtiles));
+    if (!use_prune && mtiles > 0 && mtiles < 2 * sm_count()) nsplit = (int)std::min<int64_t>(std::min<int64_t>(MAX_SPLIT, ntiles), ceil_div(2 * sm_count(), mtiles));
     const int tiles_per_split = (int)ceil_div(ntiles, nsplit);
     nsplit = (int)ceil_div(ntiles, tiles_per_split);
 
-    __half* opB = ws.get<__half>((size_t)n_pad * KS);
+    // ---- reference side: computed once per reference set when a cache is given ----
+    __half* opB = ref_ready ? static_cast<__half*>(cache->opB) : rws.get<__half>((size_t)n_pad * KS);
+    double* xnorm = ref_ready ? cache->xnorm : rws.get<double>((size_t)n_pad);
+    unsigned char* rscalars = ref_ready ? cache->scalars : rws.get<unsigned char>(64);
+    if (!rws.ok()) return B200MNN_ENOMEM;
+    unsigned int* absmax_bits = reinterpret_cast<unsigned int*>(rscalars);
+    int* scale_exp = reinterpret_cast<int*>(rscalars + 8);
+    unsigned long long* maxnorm_bits = reinterpret_cast<unsigned long long*>(rscalars + 16);
+    unsigned int* bmax_bits = reinterpret_cast<unsigned int*>(rscalars + 32);   // [2]
+    double* qnorm = nq > 0 ? ws.get<double>((size_t)nq_pad) : nullptr;
+    if (!ws.ok()) return B200MNN_ENOMEM;
+    ClusterPlan plan;
+    if (ref_ready) plan = cache->plan;
+    if (!ref_ready) {
+        B200_CUDA(cudaMemsetAsync(rscalars, 0, 64, stream));
+        rowstat_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(dX, n, d, xnorm, absmax_bits, maxnorm_bits);
+        B200_LAUNCH_CHECK();
+    }
+    if (!cache) {   // one scale for both sides; with a cache the queries do not enter the scale (see RefCache)
+        rowstat_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, stream>>>(dQ, nq, d, qnorm, absmax_bits, nullptr);
+        B200_LAUNCH_CHECK();
+    }
+    if (!ref_ready) {
+        scale_kernel<<<1, 1, 0, stream>>>(absmax_bits, maxnorm_bits, scale_exp);
+        B200_LAUNCH_CHECK();
+        if (use_prune) B200_TRY(build_ref_plan(dX, n, d, nclusters, maxnorm_bits, rws, stream, &plan));
+        prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm, nullptr, bmax_bits,
+                                                                                      use_prune ? plan.refmap : nullptr);
+        B200_LAUNCH_CHECK();
+        if (cache) {
+            cache->ready = true;
+            cache->dX = dX;
+            cache->n = n;
+            cache->d = d;
+            cache->k = k;
+            cache->use_prune = use_prune;
+            cache->opB = opB;
+            cache->xnorm = xnorm;
+            cache->scalars = rscalars;
+            cache->plan = plan;
+        }
+    }
+    if (nq == 0) return 0;   // reference side only (cache)
+
+    // ---- query side ----
     __half* opA = ws.get<__half>((size_t)nq_pad * KS);
-    double* xnorm = ws.get<double>((size_t)n_pad);
-    double* qnorm = ws.get<double>((size_t)nq_pad);
     int32_t* cand_idx = ws.get<int32_t>((size_t)nsplit * nslots * per);
     float* cand_score = dbg ? ws.get<float>((size_t)nsplit * nslots * per) : nullptr;
     float* thr = ws.get<float>((size_t)nsplit * nslots);
@@ -2091,37 +2140,26 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     unsigned char* scalars = ws.get<unsigned char>(64);
     unsigned long long* visited = ws.get<unsigned long long>(2);
     if (!ws.ok()) return B200MNN_ENOMEM;
-    unsigned int* absmax_bits = reinterpret_cast<unsigned int*>(scalars);
-    int* scale_exp = reinterpret_cast<int*>(scalars + 8);
-    unsigned long long* maxnorm_bits = reinterpret_cast<unsigned long long*>(scalars + 16);
     int* flag_count = reinterpret_cast<int*>(scalars + 24);
     int* flag_count2 = reinterpret_cast<int*>(scalars + 28);
-    unsigned int* bmax_bits = reinterpret_cast<unsigned int*>(scalars + 32);   // [2]
     B200_CUDA(cudaMemsetAsync(scalars, 0, 64, stream));
     B200_CUDA(cudaMemsetAsync(visited, 0, 16, stream));
-
-    rowstat_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(dX, n, d, xnorm, absmax_bits, maxnorm_bits);
-    B200_LAUNCH_CHECK();
-    rowstat_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, stream>>>(dQ, nq, d, qnorm, absmax_bits, nullptr);
-    B200_LAUNCH_CHECK();
-    scale_kernel<<<1, 1, 0, stream>>>(absmax_bits, maxnorm_bits, scale_exp);
-    B200_LAUNCH_CHECK();
-    ClusterPlan plan;
+    if (cache) {
+        rowstat_kernel<<<(unsigned)ceil_div(nq, 128), 128, 0, stream>>>(dQ, nq, d, qnorm, reinterpret_cast<unsigned int*>(scalars), nullptr);
+        B200_LAUNCH_CHECK();
+    }
     int2* lists2 = nullptr;
     float* qoff2 = nullptr;
     int32_t* qmap2 = nullptr;   // second tier: the uncertified queries regrouped by cluster
     int* work2 = nullptr;
     if (use_prune) {
-        B200_TRY(build_cluster_plan(dX, n, dQ, nq, d, nclusters, qnorm, scale_exp, maxnorm_bits, ws, stream, &plan));
-        lists2 = ws.get<int2>((size_t)(nslots / CL_TILE) * nclusters);
+        B200_TRY(build_query_plan(&plan, dQ, nq, d, qnorm, scale_exp, maxnorm_bits, ws, stream));
+        lists2 = ws.get<int2>((size_t)(nslots / CL_TILE) * plan.C);
         qoff2 = ws.get<float>((size_t)nslots);
         qmap2 = ws.get<int32_t>((size_t)nslots);
         work2 = ws.get<int>((size_t)3 * CL_MAXC + 4);
         if (!ws.ok()) return B200MNN_ENOMEM;
     }
-    prep_operand_kernel<false><<<(unsigned)ceil_div(n_pad, 128), 128, 0, stream>>>(dX, n, n_pad, d, L, scale_exp, opB, xnorm, nullptr, bmax_bits,
-                                                                                  use_prune ? plan.refmap : nullptr);
-    B200_LAUNCH_CHECK();
     prep_operand_kernel<true><<<(unsigned)ceil_div(nq_pad, 128), 128, 0, stream>>>(dQ, nq, nq_pad, d, L, scale_exp, opA, nullptr, qerr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
 

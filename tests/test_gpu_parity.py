@@ -249,6 +249,44 @@ def test_find_mutual_nn_matches_oracle(n1, n2, k1, k2):
     assert np.all(np.diff(res["first"]) >= 0)  # order contract: first ascending
 
 
+@pytest.mark.parametrize("col_major", [0, 1])
+@pytest.mark.parametrize("prune", ["0", "1"])
+def test_find_mutual_nn_pipelined_upload(monkeypatch, col_major, prune):
+    """Large inputs take the pipelined host entry: batch 2 is uploaded in row chunks and searched chunk by chunk against a
+    cached reference side of batch 1 (knn::RefCache; scale from the reference rows alone).  Forced here on small inputs,
+    in both host layouts, with and without the cluster plan; ragged last chunk; pairs identical to the oracle."""
+    import ctypes as C
+    from batchelor_b200 import _lib
+    monkeypatch.setenv("B200MNN_PIPELINE_MIN_ROWS", "256")
+    monkeypatch.setenv("B200MNN_PRUNE", prune)
+    n1, n2, k1, k2 = 2300, 3001, 20, 12
+    b1, b2 = synth.pc_batches(2, [n1, n2], d=50, ncomp=8)
+    b2 = b2 * 1.7   # queries of the cached search somewhat larger than its references
+    h1 = np.asfortranarray(b1) if col_major else np.ascontiguousarray(b1)
+    h2 = np.asfortranarray(b2) if col_major else np.ascontiguousarray(b2)
+    cap = n1 * k2
+    first = np.zeros(cap, np.int32); second = np.zeros(cap, np.int32)
+    npairs = C.c_int64(0)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    _lib.call("b200mnn_find_mutual_nn", fp(h1), n1, fp(h2), n2, 50, k1, k2, col_major, ip(first), ip(second), cap, C.byref(npairs))
+    f, s = capi.find_mutual_nn(b1, b2, k1, k2)
+    m = npairs.value
+    assert m == len(f) and np.array_equal(first[:m], f) and np.array_equal(second[:m], s)
+
+
+@pytest.mark.parametrize("epi", ["0", "1"])
+@pytest.mark.parametrize("n,nq,d,k", [(70000, 20000, 50, 20), (5000, 3000, 17, 24), (3000, 1000, 120, 5)])
+def test_query_knn_both_epilogues(monkeypatch, epi, n, nq, d, k):
+    """The TS kernel's two epilogues (B200MNN_EPI=1: per-thread register lists, the default; 0: replace-the-maximum lists)
+    give the same exact answer, with the cluster plan on (first shape) and off."""
+    monkeypatch.setenv("B200MNN_EPI", epi)
+    X, Q = synth.pc_batches(2, [n, nq], d=d, ncomp=6)
+    res = bb.queryKNN(X, Q, k)
+    want_i, want_d = capi.query_knn(X, Q, k)
+    assert np.array_equal(res["index"], want_i) and np.array_equal(res["distance"], want_d)
+
+
 def test_find_mutual_nns_empty_and_no_pairs():
     first, second = bb.find_mutual_nns(np.zeros((0, 3), np.int32), np.ones((4, 2), np.int32))
     assert first.size == 0 and second.size == 0
