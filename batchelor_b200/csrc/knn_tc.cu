@@ -899,11 +899,18 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
 //  * thresholds.  T = l[31] with the slot bits cleared is a lower bound (in the integer image) of every score this
 //    thread ever dropped or refused, and it only decreases.  The thread's filter is min(own T, partner's T) as a float,
 //    refreshed after every step (a stale threshold only admits more records);
+//    (Tried: a tighter per-row filter, the R-th best score of both lists together.  R = 32 doubles the queries the
+//    one-term tier cannot certify, R = 28 leaves 5 % uncertified: the certificate needs the margin the two per-list
+//    thresholds give, about the 45th best score of the row.)
 //  * at the end of the stream the two lists of a row are merged (one min/max step across the lanes): the 32 smallest
 //    are the row's candidates and thr = min(both T, smallest dropped entry), so that every scanned reference that is
 //    not a candidate has score >= thr -- the same certificate the re-rank expects.
 constexpr int SL_KEEP = 24;                          // list entries (registers) and id slots per thread (>= the largest k of E == 1)
 constexpr int SL_PREC = 16;                          // record stack entries per thread
+#ifndef B200_SL_POP
+#define B200_SL_POP 16
+#endif
+constexpr int SL_POP_LANES = B200_SL_POP;            // a step after a tile is worth it when this many lanes have a record
 constexpr int SL_ID_BYTES = SL_KEEP * 32 * 4;        // per warp: id of slot s of lane l at [s][l]
 constexpr int SL_RS_BYTES = SL_PREC * 32 * 16;       // record scores (float4 per record and lane)
 constexpr int SL_RI_BYTES = SL_PREC * 32 * 4;        // record ids
@@ -1225,7 +1232,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             }
             __syncwarp();
             uint32_t cnt = 0;    // records on this lane's stack
-            float thr = inf;     // min(own T, partner's T) as a float: what a score must beat to be recorded
+            float thr = inf;     // what a score must beat to be recorded: min(own T, partner's T) as a float
             int seq = 0, stage = 0;
             uint32_t par = 0;
             auto step = [&]() {
@@ -1257,7 +1264,11 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                 if (trace) { c2 = clock64(); acc_t[0] += c1 - c0; acc_t[1] += c2 - c1; }
                 if (dbg_mode == 1) continue;
                 // Dense scan (no cluster plan): most tiles hold no score below any threshold of the warp -- two min trees and
-                // one vote skip them.  (With pruning nearly every tile is one of the queries' own component and has hits.)
+                // one vote skip them.  With a plan nearly every tile is one of the queries' own component and has hits, so
+                // the test is not made.  (Tried: testing every 8th tile and staying in a tested mode while tiles come out
+                // quiet, for weakly separated data.  One Gaussian blob gained 5 %; the mixture lost 7-10 %, because the
+                // mode -- as a loop-carried flag or as two copies of the loop -- cost ptxas its proof that the votes of the
+                // loop are convergent.)
                 if (P.cl_list == nullptr && !__any_sync(0xffffffffu, fminf(chunk_min(v0), chunk_min(v1)) < thr)) continue;
                 const uint32_t idb = (uint32_t)tile * (uint32_t)TS_BN + (uint32_t)(lane >> 4) * 32u;   // reference of v0[0]; v1[0] is 64 further
                 // ONE copy of the step code (the loop is not unrolled); 32 scores = 8 quads need room for 8 records
@@ -1266,7 +1277,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                     // before a push: steps until every lane has room; after the tile: one step if at least half of the
                     // lanes have a record (worth it)
                     bool need = (h < 2) ? __any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 8))
-                                        : (__popc(__ballot_sync(0xffffffffu, cnt != 0u)) >= 16);
+                                        : (__popc(__ballot_sync(0xffffffffu, cnt != 0u)) >= SL_POP_LANES);
                     while (need) {
                         step();
                         need = (h < 2) && __any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 8));

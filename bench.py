@@ -510,7 +510,8 @@ def run_b200(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "fp16 tensor-core scoring (one-term tier, fp16x3 re-score of uncertified queries; fp32 accumulate) + fp64 exact re-rank", "data": "synthetic",
             "config": workload_config(args),
-            "parallelism": (f"query rows sharded over {world} GPU(s), reference batch replicated, NCCL all-gather of per-shard top-k"
+            "parallelism": (f"{world} GPUs: the two searches split over two groups of ranks, query rows sharded inside a group, reference "
+                            "batch replicated, one NCCL all-gather of the per-shard neighbour indices (device.direction_split)"
                             if world > 1 else "single GPU"),
             "mnn_pairs": npairs,
             "parity": parity,
@@ -527,7 +528,7 @@ def run_b200(args):
                          "kernel": "knn_candidates_ts_kernel<1,1> (tcgen05 TS mode: query operand in TMEM, one-term fp16 tier; its three-term launches on the uncertified queries are included)",
                          "kernel_ms_per_launch": kernel_ms_max / max(kernel_launches / world, 1),
                          "kernel_share_of_step": kernel_ms_max / total_ms,
-                         "algorithmic_flops_per_launch": 2.0 * (n1 / world) * n2 * args.dims,
+                         "algorithmic_flops_per_launch": 2.0 * (n1 * (2 if world > 1 else 1) / world) * n2 * args.dims,
                          "executed_tflops": executed, "frac_executed": executed / peaks["bf16_tflops"],
                          "executed_over_algorithmic": kernel_executed / max(kernel_flops, 1.0),
                          "note": "frac = ALGORITHMIC (brute-force) 2*nq*n*d flops of the search / summed time of the candidate-scoring "
