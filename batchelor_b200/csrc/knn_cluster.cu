@@ -22,7 +22,7 @@ namespace knn {
 namespace {
 
 constexpr int SAMPLE_MAX = 16384;   // rows of the k-means sample
-constexpr int FPS_MAX = 4096;       // rows used by the farthest-point seeding
+constexpr int FPS_MAX = 2048;       // rows used by the farthest-point seeding (one block, serial in the seeds: 0.33 ms)
 constexpr int LLOYD_ITERS = 4;
 
 __device__ __forceinline__ unsigned long long dkey(double v) {
@@ -148,12 +148,17 @@ __device__ __forceinline__ void dots(const double* __restrict__ x, int d, int C,
 // the loop is FMA-bound (one row element + 32 broadcast 16-byte loads feed 64 FMAs).
 template <int PASS>
 __device__ __forceinline__ int nearest_centroid(const double* __restrict__ x, int d, int C, const double* __restrict__ cenT,
-                                                const double* __restrict__ cnorm) {
+                                                const double* __restrict__ cnorm, double* __restrict__ dots_row = nullptr) {
     double best = INFINITY;
     int bi = 0;
     for (int c0 = 0; c0 < C; c0 += PASS) {
         double a[PASS];
         dots<PASS>(x, d, C, cenT, c0, a);
+        if (dots_row) {   // kept for the projection kernels: the same C dot products, not computed twice
+            double2* o = reinterpret_cast<double2*>(dots_row + c0);
+#pragma unroll
+            for (int u = 0; u < PASS / 2; ++u) o[u] = make_double2(a[2 * u], a[2 * u + 1]);
+        }
 #pragma unroll
         for (int u = 0; u < PASS; ++u) {
             const double sc = cnorm[c0 + u] - 2.0 * a[u];
@@ -227,7 +232,8 @@ __global__ void centroid_dist_kernel(const double* __restrict__ cen, int C, int 
 template <int PASS>
 __global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restrict__ X, int64_t n, int d, int C,
                                                        const double* __restrict__ cen, const double* __restrict__ cnorm,
-                                                       int32_t* __restrict__ cid, int* __restrict__ counts) {
+                                                       int32_t* __restrict__ cid, int* __restrict__ counts,
+                                                       double* __restrict__ dots_out /* optional [n][C]: x . c for every centroid */) {
     extern __shared__ double cenT[];   // [d][C]
     load_centroids_t(cen, C, d, cenT);
     __syncthreads();
@@ -235,7 +241,8 @@ __global__ void __launch_bounds__(CL_TILE) assign_kernel(const double* __restric
     const bool valid = i < n;
     int c = -1;
     if (valid) {
-        c = nearest_centroid<PASS>(X + i * d, d, C, cenT, cnorm);   // a warp's 32 rows are contiguous: L1 serves the strided reads
+        // a warp's 32 rows are contiguous: L1 serves the strided reads
+        c = nearest_centroid<PASS>(X + i * d, d, C, cenT, cnorm, dots_out ? dots_out + (size_t)i * C : nullptr);
         cid[i] = c;
     }
     // warp-aggregated histogram
@@ -305,7 +312,11 @@ __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __r
                                                              const double* __restrict__ cen, const double* __restrict__ cdist,
                                                              const double* __restrict__ cinv, unsigned long long* __restrict__ vref, const unsigned long long* __restrict__ maxnorm_bits,
                                                              const double* __restrict__ qnorm, const int* __restrict__ scale_exp,
-                                                             int2* __restrict__ lists, float* __restrict__ qoff) {
+                                                             int2* __restrict__ lists, float* __restrict__ qoff,
+                                                             const double* __restrict__ dots_in /* optional [rows][C] from assign_kernel */,
+                                                             const double* __restrict__ norms /* with dots_in: squared row norms */) {
+    // With dots_in the C dot products of every row come from the assignment pass (bit-identical: same FMA order) and this
+    // kernel only reduces them.  Otherwise:
     // Shared memory holds the transposed centroids only: every thread reads its (gathered) row straight from global
     // memory -- 400 contiguous bytes that stay in L1 across the passes -- so eight blocks fit an SM instead of two
     // (staging the 128 rows took 52 KB per block and left the kernel latency-bound at 8 warps per SM).
@@ -320,20 +331,35 @@ __global__ void __launch_bounds__(CL_TILE) tile_project_kernel(const double* __r
     for (int c = tid; c < CL_MAXC; c += CL_TILE) red[c] = (MODE == 0) ? dkey(-INFINITY) : dkey(INFINITY);
     __syncthreads();
     if (MODE == 0 && src_s[0] < 0) return;           // clusters are padded at their end: an empty first row = an unused tile
-    load_centroids_t(cen, C, d, cenT);
-    __syncthreads();
+    if (!dots_in) {
+        load_centroids_t(cen, C, d, cenT);
+        __syncthreads();
+    }
     const int src = src_s[tid];
     const bool valid = src >= 0;
     const int P = valid ? cid[src] : 0;
-    const double* x = X + (int64_t)(valid ? src : src_s[0] < 0 ? 0 : src_s[0]) * d;   // padding rows read a valid row; their values are discarded
+    const int64_t rsrc = valid ? src : (src_s[0] < 0 ? 0 : src_s[0]);   // padding rows read a valid row; their values are discarded
+    const double* x = X + rsrc * d;
+    const double* dr = dots_in ? dots_in + (size_t)rsrc * C : nullptr;
     const double M = sqrt(__longlong_as_double((long long)*maxnorm_bits));
     double gP = 0.0, xn = 0.0;
-    for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, cenT[t * C + P], gP); xn = fma(xv, xv, xn); }
+    if (dr) {
+        gP = dr[P];
+        xn = norms[rsrc];
+    } else {
+        for (int t = 0; t < d; ++t) { const double xv = x[t]; gP = fma(xv, cenT[t * C + P], gP); xn = fma(xv, xv, xn); }
+    }
     const double mg_num = 1e-11 * (sqrt(xn) + M) * M;   // >= 1000x the rounding error of the two dot products and the reciprocal
     const double tiny = 1e-5 * M;
     for (int c0 = 0; c0 < C; c0 += PASS) {
         double a[PASS];
-        dots<PASS>(x, d, C, cenT, c0, a);
+        if (dr) {
+            const double2* ip = reinterpret_cast<const double2*>(dr + c0);
+#pragma unroll
+            for (int u = 0; u < PASS / 2; ++u) { const double2 v2 = ip[u]; a[2 * u] = v2.x; a[2 * u + 1] = v2.y; }
+        } else {
+            dots<PASS>(x, d, C, cenT, c0, a);
+        }
 #pragma unroll
         for (int u = 0; u < PASS; ++u) {
             const int c = c0 + u;
@@ -452,8 +478,12 @@ static int set_smem(const void* fn, size_t bytes) {
     return 0;
 }
 
-int build_ref_plan(const double* dX, int64_t n, int d, int C, const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream,
-                   ClusterPlan* plan) {
+// the dot products of every row with every centroid are kept between the assignment and the projection kernels unless
+// that would take more than this many bytes (then the projection kernels compute them again)
+static const size_t kMaxDotsBytes = (size_t)6 << 30;
+
+int build_ref_plan(const double* dX, int64_t n, int d, int C, const double* xnorm, const unsigned long long* maxnorm_bits, Scratch& ws,
+                   cudaStream_t stream, ClusterPlan* plan) {
     if (C < 16 || C > CL_MAXC || (C & (C - 1)) != 0) return fail(B200MNN_EINVAL, "internal: cluster count must be a power of two in [16, 256]");
     int m = (int)std::min<int64_t>(n, SAMPLE_MAX);
     const int mf = std::min(m, FPS_MAX);
@@ -479,6 +509,8 @@ int build_ref_plan(const double* dX, int64_t n, int d, int C, const unsigned lon
     double* sums = ws.get<double>((size_t)C * d);
     int* ints = ws.get<int>((size_t)5 * CL_MAXC + 16);
     if (!ws.ok()) return B200MNN_ENOMEM;
+    Scratch tmp(stream);                   // released (stream-ordered) when this function returns
+    double* dots_ref = ((size_t)n * C * sizeof(double) <= kMaxDotsBytes) ? tmp.get<double>((size_t)n * C) : nullptr;
     int* counts = ints;                    // [C]   Lloyd counts
     p.cnt_ref = ints + CL_MAXC;            // [C]
     int* row_base = ints + 2 * CL_MAXC;    // [C]
@@ -520,8 +552,8 @@ int build_ref_plan(const double* dX, int64_t n, int d, int C, const unsigned lon
     transpose_centroids_kernel<<<(unsigned)ceil_div((int64_t)C * d, 256), 256, 0, stream>>>(p.centroids, C, d, p.centroids_t);
     B200_LAUNCH_CHECK();
 
-    if (C % 64 == 0) assign_kernel<64><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, p.cnorm, cid_ref, p.cnt_ref);
-    else assign_kernel<16><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, p.cnorm, cid_ref, p.cnt_ref);
+    if (C % 64 == 0) assign_kernel<64><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, p.cnorm, cid_ref, p.cnt_ref, dots_ref);
+    else assign_kernel<16><<<(unsigned)ceil_div(n, CL_TILE), CL_TILE, cen_smem, stream>>>(dX, n, d, C, p.centroids_t, p.cnorm, cid_ref, p.cnt_ref, dots_ref);
     B200_LAUNCH_CHECK();
     ref_offsets_kernel<<<1, 32, 0, stream>>>(p.cnt_ref, C, p.cl_tile0, row_base);
     B200_LAUNCH_CHECK();
@@ -532,10 +564,12 @@ int build_ref_plan(const double* dX, int64_t n, int d, int C, const unsigned lon
     B200_LAUNCH_CHECK();
     if (C % 64 == 0)
         tile_project_kernel<0, 64><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, cen_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
-                                                                                                p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
+                                                                                                p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr,
+                                                                                                dots_ref, xnorm);
     else
         tile_project_kernel<0, 16><<<(unsigned)(p.n_rows_max / CL_TILE), CL_TILE, cen_smem, stream>>>(dX, d, dp, C, p.refmap, nullptr, cid_ref, p.centroids_t,
-                                                                                                p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr);
+                                                                                                p.cdist, p.cinv, p.vref, maxnorm_bits, nullptr, nullptr, nullptr, nullptr,
+                                                                                                dots_ref, xnorm);
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -550,6 +584,7 @@ int build_query_plan(ClusterPlan* plan, const double* dQ, int64_t nq, int d, con
     p.qoff = ws.get<float>((size_t)p.nslots_max);
     p.cid_q = ws.get<int32_t>((size_t)nq);
     int* ints = ws.get<int>((size_t)3 * CL_MAXC + 16);
+    p.dots_q = ((size_t)nq * C * sizeof(double) <= kMaxDotsBytes) ? ws.get<double>((size_t)nq * C) : nullptr;
     if (!ws.ok()) return B200MNN_ENOMEM;
     int* cnt_q = ints;                     // [C]
     int* slot_base = ints + CL_MAXC;       // [C]
@@ -558,8 +593,8 @@ int build_query_plan(ClusterPlan* plan, const double* dQ, int64_t nq, int d, con
     B200_CUDA(cudaMemsetAsync(ints, 0, sizeof(int) * (3 * CL_MAXC + 16), stream));
     B200_CUDA(cudaMemsetAsync(p.qmap, 0xFF, sizeof(int32_t) * (size_t)p.nslots_max, stream));
     const size_t cen_smem = (size_t)C * d * sizeof(double);
-    if (C % 64 == 0) assign_kernel<64><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, p.cnorm, p.cid_q, cnt_q);
-    else assign_kernel<16><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, p.cnorm, p.cid_q, cnt_q);
+    if (C % 64 == 0) assign_kernel<64><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, p.cnorm, p.cid_q, cnt_q, p.dots_q);
+    else assign_kernel<16><<<(unsigned)ceil_div(nq, CL_TILE), CL_TILE, cen_smem, stream>>>(dQ, nq, d, C, p.centroids_t, p.cnorm, p.cid_q, cnt_q, p.dots_q);
     B200_LAUNCH_CHECK();
     query_offsets_kernel<<<1, 256, 0, stream>>>(p.cnt_ref, cnt_q, C, slot_base, p.nslots);
     B200_LAUNCH_CHECK();
@@ -590,10 +625,10 @@ int build_tile_lists(const ClusterPlan& p, const double* dQ, int d, const int32_
     const size_t row_smem = (size_t)p.C * d * sizeof(double);   // transposed centroids
     if (p.C % 64 == 0)
         tile_project_kernel<1, 64><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids_t, p.cdist,
-                                                                                             p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
+                                                                                             p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff, p.dots_q, qnorm);
     else
         tile_project_kernel<1, 16><<<(unsigned)(max_slots / CL_TILE), CL_TILE, row_smem, stream>>>(dQ, d, dp, p.C, qmap, count, p.cid_q, p.centroids_t, p.cdist,
-                                                                                             p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff);
+                                                                                             p.cinv, p.vref, maxnorm_bits, qnorm, scale_exp, lists, qoff, p.dots_q, qnorm);
     B200_LAUNCH_CHECK();
     return 0;
 }

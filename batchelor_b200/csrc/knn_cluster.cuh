@@ -33,14 +33,16 @@ struct ClusterPlan {
     int2* cl_list = nullptr;     // [nslots_max / CL_TILE][C]  (cluster, float bits of S^2 * lower_bound^2), ascending
     float* qoff = nullptr;       // [nslots_max]  S^2 ||q||^2 rounded up (-inf for padding slots)
     int32_t* cid_q = nullptr;    // [nq] cluster of every query (original order)
+    double* dots_q = nullptr;    // [nq][C] q . c for every centroid, kept from the assignment for the tile lists (may be null)
 };
 
 // Both parts are built on `stream` without host synchronisation.  Reference side: k-means on a sample, every reference row
 // assigned and grouped, the C x C extent table.  Query side (needs the reference side): every query assigned to its nearest
 // reference centroid and grouped, per query tile the sorted cluster list.  qnorm: fp64 squared norms of the queries
-// (original order); scale_exp / maxnorm_bits: the device scalars of the scoring pipeline (knn_tc.cu).
-int build_ref_plan(const double* dX, int64_t n, int d, int C, const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream,
-                   ClusterPlan* plan);
+// (original order), xnorm: those of the references; scale_exp / maxnorm_bits: the device scalars of the scoring pipeline
+// (knn_tc.cu).
+int build_ref_plan(const double* dX, int64_t n, int d, int C, const double* xnorm, const unsigned long long* maxnorm_bits, Scratch& ws,
+                   cudaStream_t stream, ClusterPlan* plan);
 int build_query_plan(ClusterPlan* plan, const double* dQ, int64_t nq, int d, const double* qnorm, const int* scale_exp,
                      const unsigned long long* maxnorm_bits, Scratch& ws, cudaStream_t stream);
 
