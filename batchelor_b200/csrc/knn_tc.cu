@@ -906,7 +906,10 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
 //    are the row's candidates and thr = min(both T, smallest dropped entry), so that every scanned reference that is
 //    not a candidate has score >= thr -- the same certificate the re-rank expects.
 constexpr int SL_KEEP = 24;                          // list entries (registers) and id slots per thread (>= the largest k of E == 1)
-constexpr int SL_PREC = 16;                          // record stack entries per thread
+#ifndef B200_SL_ONECHECK
+#define B200_SL_ONECHECK 2
+#endif
+constexpr int SL_PREC = B200_SL_ONECHECK ? 24 : 16;  // record stack entries per thread
 #ifndef B200_SL_POP
 #define B200_SL_POP 16
 #endif
@@ -1272,6 +1275,28 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                 if (P.cl_list == nullptr && !__any_sync(0xffffffffu, fminf(chunk_min(v0), chunk_min(v1)) < thr)) continue;
                 const uint32_t idb = (uint32_t)tile * (uint32_t)TS_BN + (uint32_t)(lane >> 4) * 32u;   // reference of v0[0]; v1[0] is 64 further
                 // ONE copy of the step code (the loop is not unrolled); 32 scores = 8 quads need room for 8 records
+#if B200_SL_ONECHECK == 2
+                while (__any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 16))) step();
+                sl_push32(v0, thr, idb, cnt, rs_addr, ri_addr);
+                sl_push32(v1, thr, idb + 64u, cnt, rs_addr, ri_addr);
+                if (__popc(__ballot_sync(0xffffffffu, cnt != 0u)) >= SL_POP_LANES) step();
+#elif B200_SL_ONECHECK
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    // before the tile's 64 scores (16 quads need room for 16 records): steps until every lane has room;
+                    // after the tile: one step if at least half of the lanes have a record (worth it)
+                    bool need = (h == 0) ? __any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 16))
+                                         : (__popc(__ballot_sync(0xffffffffu, cnt != 0u)) >= SL_POP_LANES);
+                    while (need) {
+                        step();
+                        need = (h == 0) && __any_sync(0xffffffffu, cnt > (uint32_t)(SL_PREC - 16));
+                    }
+                    if (h == 0) {
+                        sl_push32(v0, thr, idb, cnt, rs_addr, ri_addr);
+                        sl_push32(v1, thr, idb + 64u, cnt, rs_addr, ri_addr);
+                    }
+                }
+#else
 #pragma unroll 1
                 for (int h = 0; h < 3; ++h) {
                     // before a push: steps until every lane has room; after the tile: one step if at least half of the
@@ -1285,6 +1310,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                     if (h == 0) sl_push32(v0, thr, idb, cnt, rs_addr, ri_addr);
                     else if (h == 1) sl_push32(v1, thr, idb + 64u, cnt, rs_addr, ri_addr);
                 }
+#endif
                 if (trace) acc_t[2] += clock64() - c2;   // includes the steps (acc_t[3])
             }
             __syncwarp();
@@ -1637,19 +1663,30 @@ rerank_kernel(const double* __restrict__ X, const double* __restrict__ Q, int64_
             if (refmap && id >= 0) id = refmap[id];
             ci[r] = id;
             double acc = 0.0;
-            for (int t0 = 0; t0 < d; t0 += RR_DCH) {
+            // Cooperative staging of the 32 candidate rows through shared memory, 16 dims (one 128-byte line per row) at a
+            // time: each half-warp fetches one row per step.  The gather is latency-bound, so all 16 loads of a chunk are issued
+            // before the first store, and the loads of the NEXT chunk are in flight while this chunk's distances accumulate (a
+            // serial chain: dimension order is part of the contract).  (Tried: every lane reading the row of its own candidate
+            // with 13 independent 16-byte loads in flight -- 4.8 instead of 3.5 ms per 1M queries: 32 scattered sectors per load
+            // instruction cost more in L1 than the staging.)
+            const int sub = lane & 15, hw = lane >> 4;
+            double vv[16];
+            auto fetch = [&](const int t0) {
                 const int len = min(RR_DCH, d - t0);
-                // cooperative staging of 32 candidate rows (chunk of 16 dims = one 128-byte line per row) into shared memory:
-                // each half-warp fetches one row per step, all 16 steps independent.  (Tried: every lane reading the row of its
-                // own candidate with 13 independent 16-byte loads in flight -- 4.8 instead of 3.5 ms per 1M queries: 32
-                // scattered sectors per load instruction cost more in L1 than the staging.)
-                const int sub = lane & 15, hw = lane >> 4;
-#pragma unroll 4
+#pragma unroll
                 for (int rr = 0; rr < 16; ++rr) {
                     const int rid = __shfl_sync(0xffffffffu, id, 2 * rr + hw);
-                    if (sub < len) stage[warp][2 * rr + hw][sub] = (rid >= 0) ? X[(int64_t)rid * d + t0 + sub] : 0.0;
+                    vv[rr] = (rid >= 0 && sub < len) ? __ldg(X + (int64_t)rid * d + t0 + sub) : 0.0;
                 }
+            };
+            fetch(0);
+            for (int t0 = 0; t0 < d; t0 += RR_DCH) {
+                const int len = min(RR_DCH, d - t0);
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr)
+                    if (sub < len) stage[warp][2 * rr + hw][sub] = vv[rr];
                 __syncwarp();
+                if (t0 + RR_DCH < d) fetch(t0 + RR_DCH);   // warp-uniform
                 for (int t = 0; t < len; ++t) {
                     const double df = __dsub_rn(qv[t0 + t], stage[warp][lane][t]);
                     acc = __dadd_rn(acc, __dmul_rn(df, df));

@@ -115,10 +115,14 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
         }
     }
 }
+#ifndef B200_PARK_NS
+#define B200_PARK_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait_parked_u(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!__all_sync(0xffffffffu, mbar_try_wait_hint(bar, parity, 20000u))) {
+        if (B200_PARK_NS) __nanosleep(B200_PARK_NS);
         if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 20000000000LL) {
             if ((threadIdx.x & 31) == 0)
                 printf("b200mnn: mbarrier watchdog fired (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
