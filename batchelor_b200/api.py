@@ -740,8 +740,8 @@ def fastMNN(*batches, batch=None, k=20, prop_k=None, restrict=None, cos_norm=Tru
             auto_merge=False, min_batch_skip=0, subset_row=None, weights=None, get_variance=False, BNPARAM=None, BPPARAM=None) -> MNNResult:
     """fastMNN (R/fastMNN.R:283-331) for [genes x cells] matrices: cosineNorm -> multi-batch PCA -> reducedMNN.
 
-    The PCA front end (R/multiBatchPCA.R) is outside the accelerated path; here it is an
-    exact SVD with each batch weighted equally, enough to feed the hot path.  ``corrected`` is [cells x d]."""
+    The PCA front end is :func:`multiBatchPCA` (R/multiBatchPCA.R:211-322: batch weights, ``subset_row``, variance
+    explained; fp64 Gram matrix + ``eigh`` on the device).  ``corrected`` is [cells x d]."""
     import torch
 
     mats = [np.asarray(b, dtype=np.float64) for b in batches]
