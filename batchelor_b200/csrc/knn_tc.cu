@@ -905,7 +905,10 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
 //  * at the end of the stream the two lists of a row are merged (one min/max step across the lanes): the 32 smallest
 //    are the row's candidates and thr = min(both T, smallest dropped entry), so that every scanned reference that is
 //    not a candidate has score >= thr -- the same certificate the re-rank expects.
-constexpr int SL_KEEP = 24;                          // list entries (registers) and id slots per thread (>= the largest k of E == 1)
+#ifndef B200_SL_KEEP
+#define B200_SL_KEEP 24
+#endif
+constexpr int SL_KEEP = B200_SL_KEEP;                // list entries (registers) and id slots per thread (>= the largest k of E == 1)
 #ifndef B200_SL_ONECHECK
 #define B200_SL_ONECHECK 2
 #endif
