@@ -1795,7 +1795,8 @@ constexpr int RS_CAP = 1024;   // references a block can collect in its single-p
 __global__ void __launch_bounds__(RS_THREADS)
 rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Q, int d, int k,
               const int* __restrict__ flag_count, const int32_t* __restrict__ flag_list, const double* __restrict__ flag_dk2, int64_t nq_all,
-              int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const int use_smem) {
+              int32_t* __restrict__ out_idx, double* __restrict__ out_dist, const int use_smem,
+              const int coop_limit, const int* __restrict__ coop_left /* optional [coop_limit]: 1 = not answered by the sliced path */) {
     __shared__ double sd[RS_THREADS / 32];
     __shared__ int si[RS_THREADS / 32];
     __shared__ double pick_d;
@@ -1806,6 +1807,7 @@ rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict_
     extern __shared__ double qs_sm[];  // [d] when use_smem
     const int count = flag_list ? *flag_count : (int)nq_all;
     for (int f = blockIdx.x; f < count; f += gridDim.x) {
+        if (coop_left && f < coop_limit && coop_left[f] == 0) continue;   // answered by rescue_collect / rescue_select (block-uniform)
         const int64_t q = flag_list ? flag_list[f] : f;
         __syncthreads();
         const double* qs = use_smem ? qs_sm : Q + q * d;   // very wide rows are read through L1 instead
@@ -1854,6 +1856,97 @@ rescue_kernel(const double* __restrict__ X, int64_t n, const double* __restrict_
                     ri = (int)r;
                 }
                 const bool after = acc > pd || (acc == pd && ri > pi);  // strictly after the previous pick
+                if (after && pair_less(acc, ri, bd, bi)) { bd = acc; bi = ri; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (pair_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+            }
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { sd[threadIdx.x >> 5] = bd; si[threadIdx.x >> 5] = bi; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double fd = sd[0];
+                int fi = si[0];
+                for (int w = 1; w < RS_THREADS / 32; ++w)
+                    if (pair_less(sd[w], si[w], fd, fi)) { fd = sd[w]; fi = si[w]; }
+                pick_d = fd;
+                pick_i = fi;
+                out_idx[q * k + j] = (fi == 0x7fffffff) ? -1 : fi;
+                if (out_dist) out_dist[q * k + j] = sqrt(fd);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// A handful of flagged queries (a few exact ties in 1M cells) would leave rescue_kernel with one block per query, each
+// streaming every reference on its own: ~11 ms per query at 1M x 50.  The first RSC_FMAX flagged queries are therefore
+// answered by a SLICED scan: block (s, y) computes the exact distances of slice s of the references to the queries
+// f = y, y + gridDim.y, ... and appends those within the query's bound to a global buffer; rescue_select_kernel then picks
+// the k best per query under (distance, index).  A query without a bound, or with more than RS_CAP references inside it,
+// is left to rescue_kernel (coop_left).
+constexpr int RSC_FMAX = 1024;   // beyond this many flagged queries rescue_kernel has enough blocks of its own
+constexpr int RSC_SLICES = 148;
+constexpr int RSC_QROWS = 16;
+__global__ void __launch_bounds__(RS_THREADS)
+rescue_collect_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Q, int d, const int* __restrict__ flag_count,
+                      const int32_t* __restrict__ flag_list, const double* __restrict__ flag_dk2, int* __restrict__ gcount,
+                      double* __restrict__ gd, int* __restrict__ gi) {
+    extern __shared__ double qrow[];   // [d]
+    const int count = min(*flag_count, RSC_FMAX);
+    const int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(n, r0 + chunk);
+    for (int f = blockIdx.y; f < count; f += gridDim.y) {
+        const double bound = flag_dk2[f];
+        if (!(bound < INFINITY)) continue;   // block-uniform
+        const int64_t q = flag_list[f];
+        __syncthreads();
+        for (int t = threadIdx.x; t < d; t += blockDim.x) qrow[t] = Q[q * d + t];
+        __syncthreads();
+        for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+            const double* xv = X + r * d;
+            double acc = 0.0;
+            for (int t = 0; t < d; ++t) {
+                const double df = __dsub_rn(qrow[t], xv[t]);
+                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+            if (acc <= bound) {
+                const int pos = atomicAdd(gcount + f, 1);
+                if (pos < RS_CAP) { gd[(size_t)f * RS_CAP + pos] = acc; gi[(size_t)f * RS_CAP + pos] = (int)r; }
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(RS_THREADS)
+rescue_select_kernel(int k, const int* __restrict__ flag_count, const int32_t* __restrict__ flag_list, const double* __restrict__ flag_dk2,
+                     const int* __restrict__ gcount, const double* __restrict__ gd, const int* __restrict__ gi, int* __restrict__ coop_left,
+                     int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    __shared__ double sd[RS_THREADS / 32];
+    __shared__ int si[RS_THREADS / 32];
+    __shared__ double pick_d;
+    __shared__ int pick_i;
+    const int count = min(*flag_count, RSC_FMAX);
+    for (int f = blockIdx.x; f < count; f += gridDim.x) {
+        const int cn = gcount[f];
+        const bool ok = flag_dk2[f] < INFINITY && cn <= RS_CAP && cn >= k;   // block-uniform
+        if (threadIdx.x == 0) coop_left[f] = ok ? 0 : 1;
+        if (!ok) continue;
+        const int64_t q = flag_list[f];
+        __syncthreads();
+        if (threadIdx.x == 0) { pick_d = -1.0; pick_i = -1; }
+        __syncthreads();
+        for (int j = 0; j < k; ++j) {
+            const double pd = pick_d;
+            const int pi = pick_i;
+            double bd = INFINITY;
+            int bi = 0x7fffffff;
+            for (int r = threadIdx.x; r < cn; r += blockDim.x) {
+                const double acc = gd[(size_t)f * RS_CAP + r];
+                const int ri = gi[(size_t)f * RS_CAP + r];
+                const bool after = acc > pd || (acc == pd && ri > pi);   // strictly after the previous pick
                 if (after && pair_less(acc, ri, bd, bi)) { bd = acc; bi = ri; }
             }
 #pragma unroll
@@ -2053,7 +2146,28 @@ int launch_rescue(const double* dX, int64_t n, const double* dQ, int64_t nq, int
     int use_smem = 0;
     size_t bytes = 0;
     B200_TRY(rescue_smem(d, &use_smem, &bytes));
-    rescue_kernel<<<sm_count() * 4, RS_THREADS, bytes, stream>>>(dX, n, dQ, d, k, flag_count, flag_list, flag_dk2, nq, d_idx, d_dist, use_smem);
+    Scratch ws(stream);
+    int* coop_left = nullptr;
+    const int fmax = (int)std::min<int64_t>(nq, RSC_FMAX);
+    if (flag_dk2 && flag_list && (size_t)d * sizeof(double) <= (size_t)40 * 1024 && !getenv("B200MNN_RESCUE_SERIAL")) {
+        // sliced scan for the first RSC_FMAX flagged queries (see rescue_collect_kernel); no host synchronisation: the grids
+        // are sized for the worst case and every block reads the flag count on the device
+        int* gcount = ws.get<int>((size_t)fmax);
+        coop_left = ws.get<int>((size_t)fmax);
+        double* gd = ws.get<double>((size_t)fmax * RS_CAP);
+        int* gi = ws.get<int>((size_t)fmax * RS_CAP);
+        if (!ws.ok()) return B200MNN_ENOMEM;
+        B200_CUDA(cudaMemsetAsync(gcount, 0, sizeof(int) * (size_t)fmax, stream));
+        B200_CUDA(cudaMemsetAsync(coop_left, 0xFF, sizeof(int) * (size_t)fmax, stream));   // non-zero: left to rescue_kernel unless answered
+        const dim3 grid((unsigned)std::min<int64_t>(RSC_SLICES, std::max<int64_t>(1, n / 1024)), (unsigned)std::min(fmax, RSC_QROWS), 1);
+        rescue_collect_kernel<<<grid, RS_THREADS, (size_t)d * sizeof(double), stream>>>(dX, n, dQ, d, flag_count, flag_list, flag_dk2, gcount, gd, gi);
+        B200_LAUNCH_CHECK();
+        rescue_select_kernel<<<(unsigned)std::min(fmax, 4 * sm_count()), RS_THREADS, 0, stream>>>(k, flag_count, flag_list, flag_dk2, gcount, gd, gi,
+                                                                                                 coop_left, d_idx, d_dist);
+        B200_LAUNCH_CHECK();
+    }
+    rescue_kernel<<<sm_count() * 4, RS_THREADS, bytes, stream>>>(dX, n, dQ, d, k, flag_count, flag_list, flag_dk2, nq, d_idx, d_dist, use_smem,
+                                                                coop_left ? fmax : 0, coop_left);
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -2064,7 +2178,7 @@ int launch_rescue_all(const double* dX, int64_t n, const double* dQ, int64_t nq,
     size_t bytes = 0;
     B200_TRY(rescue_smem(d, &use_smem, &bytes));
     const int grid = (int)std::min<int64_t>(nq, (int64_t)sm_count() * 8);
-    rescue_kernel<<<grid, RS_THREADS, bytes, stream>>>(dX, n, dQ, d, k, nullptr, nullptr, nullptr, nq, d_idx, d_dist, use_smem);
+    rescue_kernel<<<grid, RS_THREADS, bytes, stream>>>(dX, n, dQ, d, k, nullptr, nullptr, nullptr, nq, d_idx, d_dist, use_smem, 0, nullptr);
     B200_LAUNCH_CHECK();
     if (d_stats) { write_stats_kernel<<<1, 1, 0, stream>>>(nullptr, d_stats, 0, 0); B200_LAUNCH_CHECK(); }
     return 0;

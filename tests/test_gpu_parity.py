@@ -197,6 +197,27 @@ def test_query_knn_many_exact_duplicates_go_through_the_bounded_rescue():
     assert np.array_equal(dist.cpu().numpy(), want_dist)
 
 
+@pytest.mark.parametrize("serial", [False, True])
+def test_query_knn_a_handful_of_rescued_queries(monkeypatch, serial):
+    """A few queries sitting on a 40-fold duplicated location in otherwise ordinary data: they alone need the exact rescue,
+    which answers the first flagged queries with a scan sliced over many blocks (one block per query would stream every
+    reference on its own); B200MNN_RESCUE_SERIAL keeps the one-block-per-query kernel.  Same exact answer either way."""
+    import torch
+    from batchelor_b200 import device as dev
+
+    if serial:
+        monkeypatch.setenv("B200MNN_RESCUE_SERIAL", "1")
+    X, Q = synth.pc_batches(2, [70_000, 17_000], d=50, ncomp=8)
+    X[100:140] = X[100]
+    Q[:5] = X[100]
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    idx, dist = dev.query_knn(torch.from_numpy(X).cuda(), torch.from_numpy(Q).cuda(), 20, stats=stats)
+    assert 5 <= int(stats[0]) < 200, "expected a handful of uncertifiable queries"
+    want_idx, want_dist = capi.Kmknn(X).query(Q, 20)
+    assert int((idx.cpu().numpy() + 1 != want_idx).sum()) == 0
+    assert np.array_equal(dist.cpu().numpy(), want_dist)
+
+
 def test_query_knn_dense_path_still_exact_at_medium_size(monkeypatch):
     monkeypatch.setenv("B200MNN_PRUNE", "0")
     X, Q = synth.pc_batches(2, [70_000, 20_000], d=50)
