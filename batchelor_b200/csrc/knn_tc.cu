@@ -988,8 +988,53 @@ __device__ __forceinline__ void sl_step(uint32_t (&l)[SL_KEEP], uint32_t* ids, c
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Split epilogue (EPI == 2): the pushers of EPI == 1 and their lists in different warps
+// ------------------------------------------------------------------------------------------------
+// EPI == 1 leaves every scheduler with two epilogue warps whose instructions each wait ~4 cycles on the one before
+// (issue slots half used, ncu).  Here warps 2..9 only READ and PUSH (TMEM -> registers -> quad records), and eight more
+// warps (11..18) only POP and INSERT: lane l of inserter warp w owns the register list of lane l of pusher warp w and is
+// fed through a single-producer single-consumer ring of SP_RING records in shared memory (head written by the pusher
+// after a block fence, tail by the inserter).  Four worker warps per scheduler instead of two; the work per tile is the
+// same plus the ring bookkeeping.  Flow control: a pusher needs 8 free slots before 32 scores; an inserter pops one
+// record per lane when at least half of its lanes have one, when some ring is more than half full (its pusher may be
+// waiting), or when the stream has ended.
+constexpr int SP_RING = 16;                               // records per ring (power of two)
+constexpr int SP_THREADS = 608;                           // 19 warps
+constexpr int SP_RS_BYTES = SP_RING * 32 * 16;
+constexpr int SP_RI_BYTES = SP_RING * 32 * 4;
+constexpr int SP_CTL_BYTES = 3 * 32 * 4 + 32;             // head[32], tail[32], thr[32], done
+constexpr int SP_WARP_BYTES = SL_ID_BYTES + SP_RS_BYTES + SP_RI_BYTES + SP_CTL_BYTES;
+
+// Pushes the quad when its minimum is below thr: record slot head & (SP_RING - 1).
+__device__ __forceinline__ void sp_push_quad(const float a, const float b, const float c, const float d, const float thr, const uint32_t id0,
+                                             uint32_t& head, const uint32_t rs_addr, const uint32_t ri_addr) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f32 m;\n\t.reg .b32 as, ai, t;\n\t"
+        "min.f32 m, %1, %2, %3;\n\t"
+        "min.f32 m, m, %4;\n\t"
+        "setp.lt.f32 p, m, %5;\n\t"
+        "and.b32 t, %0, 15;\n\t"
+        "mad.lo.u32 as, t, 512, %7;\n\t"
+        "mad.lo.u32 ai, t, 128, %8;\n\t"
+        "@p st.shared.v4.f32 [as], {%1, %2, %3, %4};\n\t"
+        "@p st.shared.u32 [ai], %6;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t}"
+        : "+r"(head)
+        : "f"(a), "f"(b), "f"(c), "f"(d), "f"(thr), "r"(id0), "r"(rs_addr), "r"(ri_addr)
+        : "memory");
+}
+__device__ __forceinline__ void sp_push32(const uint32_t (&v)[32], const float thr, const uint32_t idb, uint32_t& head, const uint32_t rs_addr,
+                                          const uint32_t ri_addr) {
+    static_assert(SP_RING == 16, "sp_push_quad masks the record count with 15");
+#pragma unroll
+    for (int i = 0; i < 32; i += 4)
+        sp_push_quad(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]), thr, idb + i, head,
+                     rs_addr, ri_addr);
+}
+
 template <int E, int NBOX, int EPI>
-__global__ void __launch_bounds__(TS_THREADS, 1)
+__global__ void __launch_bounds__(EPI == 2 ? SP_THREADS : TS_THREADS, 1)
 knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] query operand rows (global); the first NBOX*64 columns are used
                          const int a_pitch,
                          const int32_t* __restrict__ qmap,  // optional: CTA row j serves query qmap[j] (second tier: the uncertified queries)
@@ -1016,7 +1061,8 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     // EPI == 0: [8 warps][16 rows][KEEP] (score bits, id) + [8 warps][8][32] float4 staging; EPI == 1: [8 warps][SL_WARP_BYTES]
     uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);
     float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 16 * KEEP);
-    float* thr_s = EPI == 1 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * SL_WARP_BYTES)
+    float* thr_s = EPI == 2 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * SP_WARP_BYTES)
+                 : EPI == 1 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * SL_WARP_BYTES)
                             : reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                     // [128] row thresholds
     volatile int* ring = reinterpret_cast<int*>(thr_s + BM);                                                   // [TS_RING] tile ids, -1 = end
     float* qoff_s = reinterpret_cast<float*>(thr_s + BM) + TS_RING;                                            // [128]
@@ -1187,11 +1233,13 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         // Two warps per TMEM lane quarter, 16 query rows each, all 128 columns of every tile: every row has ONE candidate
         // list and one owner, so nothing is shared between warps.  tcgen05.ld 16x32bx2 hands thread t < 16 the columns
         // [c, c+32) of row t and thread t + 16 the columns [c+32, c+64) of the same row; two such loads cover a tile.
-        const int grp = (warp - 2) >> 2;          // 0: rows 0..15 of the quarter, 1: rows 16..31
-        const int q4 = warp & 3;                  // TMEM lane quarter this warp may access
+        const bool is_ins = EPI == 2 && warp >= 11;       // EPI == 2: inserter warp 11 + w serves pusher warp 2 + w
+        const int pw = is_ins ? warp - 9 : warp;          // the pusher warp of this pair
+        const int grp = (pw - 2) >> 2;            // 0: rows 0..15 of the quarter, 1: rows 16..31
+        const int q4 = pw & 3;                    // TMEM lane quarter the pusher may access
         const int row0 = q4 * 32 + grp * 16;      // first of this warp's 16 rows (CTA-relative)
-        uint2* mylist = lists + (size_t)(warp - 2) * 16 * KEEP;                      // this warp's candidate lists
-        float4* stg = stage_all + (size_t)(warp - 2) * 8 * 32;
+        uint2* mylist = lists + (size_t)(pw - 2) * 16 * KEEP;                        // this warp's candidate lists
+        float4* stg = stage_all + (size_t)(pw - 2) * 8 * 32;
         volatile float* thr_pub = thr_s + row0;                                      // read by the producer's stop test
         const uint32_t lane_acc = acc_base + ((uint32_t)row0 << 16);
         long long acc_t[4] = {0, 0, 0, 0};   // measurement aid (trace only): tfull wait, TMEM load, scan + hits
@@ -1202,7 +1250,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             for (int i = 0; i < KEEP / 2; ++i) mylist[i * 32 + lane] = make_uint2(ORD_INF, 0xFFFFFFFFu);   // empty lists: score +inf, id -1
         }
 
-        if (grp == 0) {
+        if (grp == 0 && !is_ins) {
             // this thread's query row -> TMEM (A operand of every MMA of this CTA); the warp covers the whole lane quarter
             const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
             const int64_t j = (int64_t)m0 + q4 * 32 + lane;
@@ -1222,7 +1270,158 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
         }
         __syncwarp();
 
-        if constexpr (EPI == 1) {
+        if constexpr (EPI == 2) {
+            // ---------- split epilogue (see sp_* above) ----------
+            uint8_t* wbase = reinterpret_cast<uint8_t*>(lists) + (size_t)(pw - 2) * SP_WARP_BYTES;
+            uint32_t* ids = reinterpret_cast<uint32_t*>(wbase) + lane;                            // slot s at ids[s * 32]
+            const float4* rs = reinterpret_cast<const float4*>(wbase + SL_ID_BYTES) + lane;       // record j at rs[j * 32]
+            const uint32_t* ri = reinterpret_cast<const uint32_t*>(wbase + SL_ID_BYTES + SP_RS_BYTES) + lane;
+            volatile uint32_t* headp = reinterpret_cast<volatile uint32_t*>(wbase + SL_ID_BYTES + SP_RS_BYTES + SP_RI_BYTES) + lane;
+            volatile uint32_t* tailp = headp + 32;
+            volatile float* thrp = reinterpret_cast<volatile float*>(headp + 64);
+            volatile uint32_t* donep = reinterpret_cast<volatile uint32_t*>(wbase + SL_ID_BYTES + SP_RS_BYTES + SP_RI_BYTES) + 96;   // one word per pair
+            const float inf = __int_as_float(0x7f800000);
+            if (!is_ins) {
+                *headp = 0u;
+                *tailp = 0u;
+                *thrp = inf;
+                if (lane == 0) *donep = 0u;
+            }
+            // pair barrier: the control words are initialised before either side looks at them (named barrier 1 + pair)
+            __syncwarp();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + (pw - 2)) : "memory");
+            if (!is_ins) {
+                // ===== pusher =====
+                const uint32_t rs_addr = smem_u32(rs), ri_addr = smem_u32(ri);
+                uint32_t head = 0u;
+                int seq = 0, stage = 0;
+                uint32_t par = 0;
+                while (true) {
+                    mbar_wait_u(smem_u32(&tfull[stage]), par);
+                    tc_fence_after();
+                    const int tile = ring[seq & (TS_RING - 1)];
+                    if (tile < 0) break;
+                    const uint32_t tbase = lane_acc + (uint32_t)(stage * TS_BN);
+                    tmem_ld16x2(tbase, v0);
+                    tmem_ld16x2(tbase + 64u, v1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&tempty[stage]));
+                    if (++stage == TS_STAGES) { stage = 0; par ^= 1u; }
+                    ++seq;
+                    if (dbg_mode == 1) continue;
+                    const float thr = *thrp;
+                    if (P.cl_list == nullptr && !__any_sync(0xffffffffu, fminf(chunk_min(v0), chunk_min(v1)) < thr)) continue;   // quiet tile of a dense scan
+                    const uint32_t idb = (uint32_t)tile * (uint32_t)TS_BN + (uint32_t)(lane >> 4) * 32u;
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        // 32 scores = 8 quads need 8 free slots of the ring
+                        if (__any_sync(0xffffffffu, head - *tailp > (uint32_t)(SP_RING - 8))) {
+                            const long long t0 = clock64();
+                            while (__any_sync(0xffffffffu, head - *tailp > (uint32_t)(SP_RING - 8))) {
+                                __nanosleep(40);
+                                if (clock64() - t0 > 20000000000LL) {
+                                    if (lane == 0) printf("b200mnn: record ring watchdog fired (block %d warp %d)\n", blockIdx.x, warp);
+                                    __trap();
+                                }
+                            }
+                        }
+                        if (h == 0) sp_push32(v0, thr, idb, head, rs_addr, ri_addr);
+                        else sp_push32(v1, thr, idb + 64u, head, rs_addr, ri_addr);
+                        __threadfence_block();   // the records before the count
+                        *headp = head;
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) *donep = 1u;
+                tc_fence_before();
+            } else {
+                // ===== inserter =====
+                uint32_t l[SL_KEEP];   // ascending keys: (order image of the score & ~31) | slot; empty = image of +inf
+#pragma unroll
+                for (int i = 0; i < SL_KEEP; ++i) {
+                    l[i] = ORD_INF | (uint32_t)i;
+                    ids[i * 32] = 0xFFFFFFFFu;   // id -1
+                }
+                __syncwarp();
+                uint32_t tail = 0u;
+                float thr = inf;
+                const long long t_start = clock64();
+                while (true) {
+                    const bool done = __any_sync(0xffffffffu, *donep != 0u);   // read BEFORE the counts: a set flag means the counts below are final
+                    __threadfence_block();
+                    const uint32_t avail = *headp - tail;
+                    const unsigned have = __ballot_sync(0xffffffffu, avail != 0u);
+                    const bool urgent = __any_sync(0xffffffffu, avail > (uint32_t)(SP_RING - 8));
+                    if (have == 0u) {
+                        if (done) break;
+                        __nanosleep(20);
+                        if (clock64() - t_start > 40000000000LL) __trap();
+                        continue;
+                    }
+                    if (!(urgent || done || __popc(have) >= SL_POP_LANES)) { __nanosleep(20); continue; }
+                    __threadfence_block();   // the counts before the records
+                    // one record per lane that has one
+                    const bool mine = avail != 0u;
+                    const uint32_t j = tail & (uint32_t)(SP_RING - 1);
+                    float4 sc = rs[j * 32];
+                    const uint32_t id0 = ri[j * 32];
+                    if (!mine) sc = make_float4(inf, inf, inf, inf);
+                    tail += mine ? 1u : 0u;
+                    float lim = thr;
+#pragma unroll 1
+                    while (true) {
+                        const float cm = fminf(fmin3(sc.x, sc.y, sc.z), sc.w);
+                        const bool act = cm < lim;
+                        if (!__any_sync(0xffffffffu, act)) break;
+                        const uint32_t q = (cm == sc.x) ? 0u : ((cm == sc.y) ? 1u : ((cm == sc.z) ? 2u : 3u));
+                        sc.x = (q == 0u) ? inf : sc.x;
+                        sc.y = (q == 1u) ? inf : sc.y;
+                        sc.z = (q == 2u) ? inf : sc.z;
+                        sc.w = (q == 3u) ? inf : sc.w;
+                        const uint32_t slot = l[SL_KEEP - 1] & SL_SLOT_MASK;
+                        const uint32_t key = (ord_bits(cm) & ~SL_SLOT_MASK) | slot;
+                        if (act) ids[slot * 32] = id0 + q;
+                        sl_insert(l, act ? key : 0xFFFFFFFFu);
+                        lim = fminf(lim, ord_float(l[SL_KEEP - 1] & ~SL_SLOT_MASK));
+                    }
+                    __syncwarp();
+                    *tailp = tail;   // the record slot may be reused
+                    const float own = ord_float(l[SL_KEEP - 1] & ~SL_SLOT_MASK);
+                    thr = fminf(own, __shfl_xor_sync(0xffffffffu, own, 16));
+                    *thrp = thr;
+                    if (lane < 16) thr_pub[lane] = thr;
+                }
+                __syncwarp();
+                // Output: as EPI == 1, by the inserter (the keys go over the record ring, which is empty now)
+                uint32_t* keys = reinterpret_cast<uint32_t*>(wbase + SL_ID_BYTES);   // [SL_KEEP entries][32 lanes]
+#pragma unroll
+                for (int i = 0; i < SL_KEEP; ++i) keys[i * 32 + lane] = l[i];
+                __syncwarp();
+                const uint32_t* idw = reinterpret_cast<const uint32_t*>(wbase);      // [32 slots][32 lanes]
+                const int64_t rowbase = (int64_t)m0 + row0;
+                const int64_t sbase = (int64_t)blockIdx.y * nq;
+#pragma unroll 1
+                for (int r = 0; r < 16; ++r) {
+                    const int64_t row = rowbase + r;
+                    if (row >= nq_eff) break;   // warp-uniform
+                    const uint32_t ka = lane < SL_KEEP ? keys[lane * 32 + r] : 0xFFFFFFFFu;
+                    const uint32_t kb = 31 - lane < SL_KEEP ? keys[(31 - lane) * 32 + r + 16] : 0xFFFFFFFFu;
+                    const bool alo = ka <= kb;
+                    const uint32_t lo = alo ? ka : kb, hi = alo ? kb : ka;
+                    const uint32_t id = idw[(lo & SL_SLOT_MASK) * 32 + (alo ? r : r + 16)];
+                    const uint32_t dropped = __reduce_min_sync(0xffffffffu, hi & ~SL_SLOT_MASK);
+                    const uint32_t ta = __shfl_sync(0xffffffffu, l[SL_KEEP - 1], r) & ~SL_SLOT_MASK;
+                    const uint32_t tb = __shfl_sync(0xffffffffu, l[SL_KEEP - 1], r + 16) & ~SL_SLOT_MASK;
+                    const int64_t o = (sbase + row) * KEEP + lane;
+                    cand_idx[o] = (int32_t)id;
+                    if (cand_score) cand_score[o] = ord_float(lo & ~SL_SLOT_MASK);
+                    if (lane == 0) thr_out[sbase + row] = ord_float(min(min(ta, tb), dropped));
+                }
+            }
+        } else if constexpr (EPI == 1) {
             // ---------- per-thread epilogue (see sl_* above) ----------
             uint8_t* wbase = reinterpret_cast<uint8_t*>(lists) + (size_t)(warp - 2) * SL_WARP_BYTES;
             uint32_t* ids = reinterpret_cast<uint32_t*>(wbase) + lane;                            // slot s at ids[s * 32]
@@ -2048,7 +2247,8 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 }
 
 static size_t ts_smem_bytes(int nslot, int E, int epi = 0) {
-    const size_t lists = epi == 1 ? (size_t)TS_EPI_WARPS * SL_WARP_BYTES
+    const size_t lists = epi == 2 ? (size_t)TS_EPI_WARPS * SP_WARP_BYTES
+                       : epi == 1 ? (size_t)TS_EPI_WARPS * SL_WARP_BYTES
                                   : (size_t)TS_EPI_WARPS * 16 * (32 * E) * 8 + (size_t)TS_EPI_WARPS * 8 * 32 * 16;
     return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + lists + (size_t)BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
            (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
@@ -2228,7 +2428,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     // Epilogue of the TS kernel: per-thread heaps (lists of 32, the default) or the replace-the-maximum lists
     // (lists of 64, B200MNN_EPI=0, or when the heaps do not fit next to the reference boxes).
     const char* eenv = getenv("B200MNN_EPI");
-    const int epi = (use_ts && E == 1 && ts_variant_fits(L.nbox, E, 1) && !(eenv && atoi(eenv) == 0)) ? 1 : 0;
+    int epi = (use_ts && E == 1 && ts_variant_fits(L.nbox, E, 1) && !(eenv && atoi(eenv) == 0)) ? 1 : 0;
+    if (epi == 1 && eenv && atoi(eenv) == 2) epi = 2;   // split epilogue (pushers and inserters in different warps): experimental
     // Pruned search (knn_cluster.cuh): reference rows grouped by a coarse k-means, query rows grouped by nearest centroid,
     // whole clusters skipped by a rigorous lower bound.  B200MNN_PRUNE=0 never, =1 whenever the shape allows, unset: for
     // searches large enough to pay for the clustering.  B200MNN_CLUSTERS sets the number of clusters (power of two).
@@ -2390,7 +2591,7 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
         if (dbg_ts) B200_CUDA(cudaMemsetAsync(dbg_ts, 0, sizeof(long long) * (64 * 32 + 64), stream));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)round_up(mtiles, csize), (unsigned)nsplit, 1);   // padding CTAs see only zero-filled query rows
-        cfg.blockDim = dim3(use_ts ? TS_THREADS : NUM_THREADS, 1, 1);
+        cfg.blockDim = dim3(use_ts ? (epi == 2 ? SP_THREADS : TS_THREADS) : NUM_THREADS, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
@@ -2422,7 +2623,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     } while (0)
 #define B200_LAUNCH_TS_E(NB)                       \
     do {                                           \
-        if (epi == 1) B200_LAUNCH_TS(1, NB, 1);    \
+        if (epi == 2) B200_LAUNCH_TS(1, NB, 2);    \
+        else if (epi == 1) B200_LAUNCH_TS(1, NB, 1);    \
         else if (E == 1) B200_LAUNCH_TS(1, NB, 0); \
         else B200_LAUNCH_TS(2, NB, 0);             \
     } while (0)
