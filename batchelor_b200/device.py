@@ -166,6 +166,44 @@ def find_mutual_nns(left: torch.Tensor, right: torch.Tensor) -> Tuple[torch.Tens
     return first[:m], second[:m]
 
 
+def gather_pair_blocks(first_l: torch.Tensor, second_l: torch.Tensor, world: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exchange step of the row-sharded pair extraction (backend-agnostic): every rank holds the pairs of its block of batch-1
+    rows (already in the reference's order, `first` in global numbering); the blocks have different lengths, so the counts are
+    all-gathered first, the blocks padded to the longest, all-gathered, and the valid parts concatenated in rank order -- which
+    IS the reference's order, because the row blocks are contiguous and ascending."""
+    import torch.distributed as dist_
+
+    cnt = torch.tensor([first_l.shape[0]], dtype=torch.int64, device=first_l.device)
+    counts = torch.empty((world,), dtype=torch.int64, device=first_l.device)
+    dist_.all_gather_into_tensor(counts, cnt)
+    counts_h = counts.tolist()
+    m = max(1, max(counts_h))
+    pad = torch.zeros((2, m), dtype=torch.int32, device=first_l.device)
+    pad[0, : first_l.shape[0]] = first_l
+    pad[1, : second_l.shape[0]] = second_l
+    full = torch.empty((world, 2, m), dtype=torch.int32, device=first_l.device)
+    dist_.all_gather_into_tensor(full.view(world * 2, m), pad)
+    first = torch.cat([full[r, 0, : counts_h[r]] for r in range(world)])
+    second = torch.cat([full[r, 1, : counts_h[r]] for r in range(world)])
+    return first, second
+
+
+def find_mutual_nns_sharded(w21: torch.Tensor, w12: torch.Tensor, world: int, rank: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Pair extraction over ranks: rank r probes its contiguous block of batch-1 rows (the probes into w12 are the work) and
+    the per-block pair lists are exchanged (:func:`gather_pair_blocks`).  Every rank ends with the full lists."""
+    n1 = w21.shape[0]
+    lo, hi, _ = shard_bounds(n1, world, rank)
+    if hi > lo:
+        # the extraction identifies a batch-1 row by its position in `left`: shift the ids in w12 so that the block's rows
+        # are 0 .. hi-lo-1 (ids outside the block then match nothing)
+        f, s2 = find_mutual_nns(w21[lo:hi], w12 - lo if lo else w12)
+        f = f + lo
+    else:
+        f = torch.zeros((0,), dtype=torch.int32, device=w21.device)
+        s2 = torch.zeros((0,), dtype=torch.int32, device=w21.device)
+    return gather_pair_blocks(f.to(torch.int32), s2.to(torch.int32), world)
+
+
 _side_streams = {}
 
 
@@ -228,7 +266,7 @@ def find_mutual_nn(data1: torch.Tensor, data2: torch.Tensor, k1: int, k2: int, s
         else:
             mine, _ = query_knn(data1, data2[lo:hi], k1, want_dist=False)   # neighbours of batch-2 cells in batch 1
         w21, w12 = direction_split_gather(mine, n1, k2, n2, k1, ws)
-        first, second = find_mutual_nns(w21, w12)
+        first, second = find_mutual_nns_sharded(w21, w12, ws, dist_.get_rank())
         return first, second, w21, w12
     split1 = ws > 1 and n1 >= ws * 2048     # batch-1 cells are the queries of the first search
     split2 = ws > 1 and n2 >= ws * 2048

@@ -81,6 +81,16 @@ def _worker_split(rank, world, port, n1, n2, k1, k2, out_dir):
     w21, w12 = dev.direction_split_gather(torch.from_numpy(np.ascontiguousarray(idx.astype(np.int32))), n1, k2, n2, k1, world)
     np.save(os.path.join(out_dir, f"w21_{rank}.npy"), w21.numpy())
     np.save(os.path.join(out_dir, f"w12_{rank}.npy"), w12.numpy())
+    # row-sharded pair extraction: this rank's block of batch-1 rows through the CPU oracle, then the exchange
+    lo, hi, _ = dev.shard_bounds(n1, world, rank)
+    if hi > lo:
+        f, s = capi.find_mutual_nns(np.asfortranarray(w21.numpy()[lo:hi] + 1), np.asfortranarray(w12.numpy() + 1 - lo))
+        f = f - 1 + lo; s = s - 1
+    else:
+        f = np.zeros(0, np.int32); s = np.zeros(0, np.int32)
+    first, second = dev.gather_pair_blocks(torch.from_numpy(f.astype(np.int32)), torch.from_numpy(s.astype(np.int32)), world)
+    np.save(os.path.join(out_dir, f"first_{rank}.npy"), first.numpy())
+    np.save(os.path.join(out_dir, f"second_{rank}.npy"), second.numpy())
     dist.destroy_process_group()
 
 
@@ -94,9 +104,12 @@ def test_direction_split_gloo(tmp_path, world, n1, n2, k1, k2):
     A, B = synth.pc_batches(2, [n1, n2], d=12, ncomp=4)
     want21 = capi.query_knn(B, A, k2)[0] - 1
     want12 = capi.query_knn(A, B, k1)[0] - 1
+    wf, ws_ = capi.find_mutual_nns(np.asfortranarray(want21 + 1), np.asfortranarray(want12 + 1))
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"w21_{r}.npy"), want21)
         assert np.array_equal(np.load(tmp_path / f"w12_{r}.npy"), want12)
+        assert np.array_equal(np.load(tmp_path / f"first_{r}.npy"), wf - 1)     # the reference's order survives the row sharding
+        assert np.array_equal(np.load(tmp_path / f"second_{r}.npy"), ws_ - 1)
     # the split covers both directions with contiguous blocks for every world size
     for w in (2, 3, 4, 8):
         for (a, b) in ((1000, 1000), (10, 100000), (100000, 10)):
