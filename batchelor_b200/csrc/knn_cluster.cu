@@ -23,7 +23,10 @@ namespace {
 
 constexpr int SAMPLE_MAX = 16384;   // rows of the k-means sample
 constexpr int FPS_MAX = 2048;       // rows used by the farthest-point seeding (one block, serial in the seeds: 0.33 ms)
-constexpr int LLOYD_ITERS = 4;
+#ifndef B200_LLOYD_ITERS
+#define B200_LLOYD_ITERS 4
+#endif
+constexpr int LLOYD_ITERS = B200_LLOYD_ITERS;
 
 __device__ __forceinline__ unsigned long long dkey(double v) {
     const long long b = __double_as_longlong(v);

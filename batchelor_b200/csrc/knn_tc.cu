@@ -922,6 +922,12 @@ constexpr int SL_RS_BYTES = SL_PREC * 32 * 16;       // record scores (float4 pe
 constexpr int SL_RI_BYTES = SL_PREC * 32 * 4;        // record ids
 constexpr int SL_WARP_BYTES = SL_ID_BYTES + SL_RS_BYTES + SL_RI_BYTES;
 constexpr uint32_t SL_SLOT_MASK = 31u;
+// Lists of 64 candidates per row (E == 2, k = 25 .. SL_KMAX2): 32 entries per thread, and the 2 x 32 entries of a row ARE its
+// candidates (no merge at the end).  Larger k keeps the replace-the-maximum lists.
+constexpr int SL_KEEP2 = 32;
+constexpr int SL_KMAX2 = 30;
+__host__ __device__ constexpr int sl_keep(int E) { return E == 1 ? SL_KEEP : SL_KEEP2; }
+__host__ __device__ constexpr int sl_warp_bytes(int E) { return sl_keep(E) * 32 * 4 + SL_RS_BYTES + SL_RI_BYTES; }
 
 // Pushes the quad (a, b, c, d) = scores of references id0 .. id0 + 3 when its minimum is below thr.
 // cnt: this lane's record count; rs_addr / ri_addr: shared-memory addresses of this lane's record 0 (scores / id).
@@ -950,14 +956,16 @@ __device__ __forceinline__ void sl_push32(const uint32_t (&v)[32], const float t
                      rs_addr, ri_addr);
 }
 // Inserts key v into the ascending register list (v = ~0: nothing happens); the largest entry drops out.
-__device__ __forceinline__ void sl_insert(uint32_t (&l)[SL_KEEP], const uint32_t v) {
+template <int LK>
+__device__ __forceinline__ void sl_insert(uint32_t (&l)[LK], const uint32_t v) {
 #pragma unroll
-    for (int i = SL_KEEP - 1; i >= 1; --i) l[i] = max(l[i - 1], min(l[i], v));
+    for (int i = LK - 1; i >= 1; --i) l[i] = max(l[i - 1], min(l[i], v));
     l[0] = min(l[0], v);
 }
 // One step: every lane with a record pops its top record and inserts the scores that are below its threshold.
 // cnt: this lane's record count; ids: this lane's slot table (slot s at ids[s * 32]); all lanes of the warp take part.
-__device__ __forceinline__ void sl_step(uint32_t (&l)[SL_KEEP], uint32_t* ids, const float4* rs, const uint32_t* ri, uint32_t& cnt, const float thr,
+template <int LK>
+__device__ __forceinline__ void sl_step(uint32_t (&l)[LK], uint32_t* ids, const float4* rs, const uint32_t* ri, uint32_t& cnt, const float thr,
                                         long long* stat) {
     const bool have = cnt > 0u;
     const uint32_t j = have ? cnt - 1u : 0u;
@@ -979,11 +987,11 @@ __device__ __forceinline__ void sl_step(uint32_t (&l)[SL_KEEP], uint32_t* ids, c
         s.y = (q == 1u) ? inf : s.y;
         s.z = (q == 2u) ? inf : s.z;
         s.w = (q == 3u) ? inf : s.w;
-        const uint32_t slot = l[SL_KEEP - 1] & SL_SLOT_MASK;          // the entry that drops out hands over its slot
+        const uint32_t slot = l[LK - 1] & SL_SLOT_MASK;               // the entry that drops out hands over its slot
         const uint32_t key = (ord_bits(cm) & ~SL_SLOT_MASK) | slot;    // < own T (multiple of 32) whenever act
         if (act) ids[slot * 32] = id0 + q;
         sl_insert(l, act ? key : 0xFFFFFFFFu);
-        lim = fminf(lim, ord_float(l[SL_KEEP - 1] & ~SL_SLOT_MASK));
+        lim = fminf(lim, ord_float(l[LK - 1] & ~SL_SLOT_MASK));
     }
     __syncwarp();
 }
@@ -1062,7 +1070,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
     uint2* lists = reinterpret_cast<uint2*>(smB + (size_t)nslot * TS_B_BOX_BYTES);
     float4* stage_all = reinterpret_cast<float4*>(lists + (size_t)TS_EPI_WARPS * 16 * KEEP);
     float* thr_s = EPI == 2 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * SP_WARP_BYTES)
-                 : EPI == 1 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * SL_WARP_BYTES)
+                 : EPI == 1 ? reinterpret_cast<float*>(smB + (size_t)nslot * TS_B_BOX_BYTES + (size_t)TS_EPI_WARPS * sl_warp_bytes(E))
                             : reinterpret_cast<float*>(stage_all + TS_EPI_WARPS * 8 * 32);                     // [128] row thresholds
     volatile int* ring = reinterpret_cast<int*>(thr_s + BM);                                                   // [TS_RING] tile ids, -1 = end
     float* qoff_s = reinterpret_cast<float*>(thr_s + BM) + TS_RING;                                            // [128]
@@ -1423,15 +1431,17 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             }
         } else if constexpr (EPI == 1) {
             // ---------- per-thread epilogue (see sl_* above) ----------
-            uint8_t* wbase = reinterpret_cast<uint8_t*>(lists) + (size_t)(warp - 2) * SL_WARP_BYTES;
+            uint8_t* wbase = reinterpret_cast<uint8_t*>(lists) + (size_t)(warp - 2) * sl_warp_bytes(E);
+            constexpr int LK = sl_keep(E);              // list entries per thread
+            constexpr int ID_BYTES = LK * 32 * 4;
             uint32_t* ids = reinterpret_cast<uint32_t*>(wbase) + lane;                            // slot s at ids[s * 32]
-            const float4* rs = reinterpret_cast<const float4*>(wbase + SL_ID_BYTES) + lane;       // record j at rs[j * 32]
-            const uint32_t* ri = reinterpret_cast<const uint32_t*>(wbase + SL_ID_BYTES + SL_RS_BYTES) + lane;
+            const float4* rs = reinterpret_cast<const float4*>(wbase + ID_BYTES) + lane;       // record j at rs[j * 32]
+            const uint32_t* ri = reinterpret_cast<const uint32_t*>(wbase + ID_BYTES + SL_RS_BYTES) + lane;
             const uint32_t rs_addr = smem_u32(rs), ri_addr = smem_u32(ri);
             const float inf = __int_as_float(0x7f800000);
-            uint32_t l[SL_KEEP];   // ascending keys: (order image of the score & ~31) | slot; empty = image of +inf
+            uint32_t l[LK];   // ascending keys: (order image of the score & ~31) | slot; empty = image of +inf
 #pragma unroll
-            for (int i = 0; i < SL_KEEP; ++i) {
+            for (int i = 0; i < LK; ++i) {
                 l[i] = ORD_INF | (uint32_t)i;
                 ids[i * 32] = 0xFFFFFFFFu;   // id -1
             }
@@ -1444,7 +1454,7 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
                 long long td = 0;
                 if (trace) td = clock64();
                 sl_step(l, ids, rs, ri, cnt, thr, trace ? stat : nullptr);
-                const float own = ord_float(l[SL_KEEP - 1] & ~SL_SLOT_MASK);
+                const float own = ord_float(l[LK - 1] & ~SL_SLOT_MASK);
                 thr = fminf(own, __shfl_xor_sync(0xffffffffu, own, 16));
                 if (lane < 16) thr_pub[lane] = thr;
                 if (trace) acc_t[3] += clock64() - td;
@@ -1525,31 +1535,41 @@ knn_candidates_ts_kernel(const __half* __restrict__ opA,   // [nq_pad][a_pitch] 
             }
             // Output.  The register lists go to shared memory (over the record stacks, which are empty now); row r of this
             // warp then merges the ascending lists of lanes r and r + 16: the 32 smallest of the 64 keys.
-            static_assert(2 * SL_KEEP >= 32 && SL_KEEP <= 32, "the merge below fills 32 output slots from two lists");
-            uint32_t* keys = reinterpret_cast<uint32_t*>(wbase + SL_ID_BYTES);   // [SL_KEEP entries][32 lanes]
+            static_assert(2 * SL_KEEP >= 32 && SL_KEEP <= 32 && SL_KEEP2 == 32, "the output below fills 32 / 64 slots from two lists");
+            uint32_t* keys = reinterpret_cast<uint32_t*>(wbase + ID_BYTES);   // [LK entries][32 lanes]
 #pragma unroll
-            for (int i = 0; i < SL_KEEP; ++i) keys[i * 32 + lane] = l[i];
+            for (int i = 0; i < LK; ++i) keys[i * 32 + lane] = l[i];
             __syncwarp();
-            const uint32_t* idw = reinterpret_cast<const uint32_t*>(wbase);      // [32 slots][32 lanes]
+            const uint32_t* idw = reinterpret_cast<const uint32_t*>(wbase);      // [LK slots][32 lanes]
             const int64_t rowbase = (int64_t)m0 + row0;
             const int64_t sbase = (int64_t)blockIdx.y * nq;
 #pragma unroll 1
             for (int r = 0; r < 16; ++r) {
                 const int64_t row = rowbase + r;
                 if (row >= nq_eff) break;   // warp-uniform
-                // a ascending in lanes 0 .. SL_KEEP-1, b descending in lanes 32-SL_KEEP .. 31, ~0 elsewhere: bitonic split
-                const uint32_t ka = lane < SL_KEEP ? keys[lane * 32 + r] : 0xFFFFFFFFu;
-                const uint32_t kb = 31 - lane < SL_KEEP ? keys[(31 - lane) * 32 + r + 16] : 0xFFFFFFFFu;
-                const bool alo = ka <= kb;
-                const uint32_t lo = alo ? ka : kb, hi = alo ? kb : ka;
-                const uint32_t id = idw[(lo & SL_SLOT_MASK) * 32 + (alo ? r : r + 16)];
-                const uint32_t dropped = __reduce_min_sync(0xffffffffu, hi & ~SL_SLOT_MASK);     // lower bound of the dropped scores
-                const uint32_t ta = __shfl_sync(0xffffffffu, l[SL_KEEP - 1], r) & ~SL_SLOT_MASK;
-                const uint32_t tb = __shfl_sync(0xffffffffu, l[SL_KEEP - 1], r + 16) & ~SL_SLOT_MASK;
-                const int64_t o = (sbase + row) * KEEP + lane;
-                cand_idx[o] = (int32_t)id;                            // empty entries carry id -1
-                if (cand_score) cand_score[o] = ord_float(lo & ~SL_SLOT_MASK);
-                if (lane == 0) thr_out[sbase + row] = ord_float(min(min(ta, tb), dropped));
+                const uint32_t ta = __shfl_sync(0xffffffffu, l[LK - 1], r) & ~SL_SLOT_MASK;
+                const uint32_t tb = __shfl_sync(0xffffffffu, l[LK - 1], r + 16) & ~SL_SLOT_MASK;
+                if constexpr (E == 2) {
+                    // 64 candidates per row: both lists as they are
+                    const uint32_t ka = keys[lane * 32 + r], kb = keys[lane * 32 + r + 16];
+                    const int64_t o = (sbase + row) * KEEP + lane;
+                    cand_idx[o] = (int32_t)idw[(ka & SL_SLOT_MASK) * 32 + r];
+                    cand_idx[o + 32] = (int32_t)idw[(kb & SL_SLOT_MASK) * 32 + r + 16];
+                    if (cand_score) { cand_score[o] = ord_float(ka & ~SL_SLOT_MASK); cand_score[o + 32] = ord_float(kb & ~SL_SLOT_MASK); }
+                    if (lane == 0) thr_out[sbase + row] = ord_float(min(ta, tb));
+                } else {
+                    // a ascending in lanes 0 .. SL_KEEP-1, b descending in lanes 32-SL_KEEP .. 31, ~0 elsewhere: bitonic split
+                    const uint32_t ka = lane < LK ? keys[lane * 32 + r] : 0xFFFFFFFFu;
+                    const uint32_t kb = 31 - lane < LK ? keys[(31 - lane) * 32 + r + 16] : 0xFFFFFFFFu;
+                    const bool alo = ka <= kb;
+                    const uint32_t lo = alo ? ka : kb, hi = alo ? kb : ka;
+                    const uint32_t id = idw[(lo & SL_SLOT_MASK) * 32 + (alo ? r : r + 16)];
+                    const uint32_t dropped = __reduce_min_sync(0xffffffffu, hi & ~SL_SLOT_MASK);     // lower bound of the dropped scores
+                    const int64_t o = (sbase + row) * KEEP + lane;
+                    cand_idx[o] = (int32_t)id;                            // empty entries carry id -1
+                    if (cand_score) cand_score[o] = ord_float(lo & ~SL_SLOT_MASK);
+                    if (lane == 0) thr_out[sbase + row] = ord_float(min(min(ta, tb), dropped));
+                }
             }
             tc_fence_before();
         } else {
@@ -2248,7 +2268,7 @@ static int make_operand_map(CUtensorMap* map, const __half* base, int64_t rows, 
 
 static size_t ts_smem_bytes(int nslot, int E, int epi = 0) {
     const size_t lists = epi == 2 ? (size_t)TS_EPI_WARPS * SP_WARP_BYTES
-                       : epi == 1 ? (size_t)TS_EPI_WARPS * SL_WARP_BYTES
+                       : epi == 1 ? (size_t)TS_EPI_WARPS * sl_warp_bytes(E)
                                   : (size_t)TS_EPI_WARPS * 16 * (32 * E) * 8 + (size_t)TS_EPI_WARPS * 8 * 32 * 16;
     return (size_t)1024 /* alignment slack */ + (size_t)nslot * TS_B_BOX_BYTES + lists + (size_t)BM * 4 + (size_t)TS_RING * 4 + (size_t)BM * 4 +
            (size_t)(2 * MAX_SLOTS + 1 + 2 * TS_STAGES) * 8 + 16;
@@ -2428,8 +2448,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
     // Epilogue of the TS kernel: per-thread heaps (lists of 32, the default) or the replace-the-maximum lists
     // (lists of 64, B200MNN_EPI=0, or when the heaps do not fit next to the reference boxes).
     const char* eenv = getenv("B200MNN_EPI");
-    int epi = (use_ts && E == 1 && ts_variant_fits(L.nbox, E, 1) && !(eenv && atoi(eenv) == 0)) ? 1 : 0;
-    if (epi == 1 && eenv && atoi(eenv) == 2) epi = 2;   // split epilogue (pushers and inserters in different warps): experimental
+    int epi = (use_ts && (E == 1 || k <= SL_KMAX2) && ts_variant_fits(L.nbox, E, 1) && !(eenv && atoi(eenv) == 0)) ? 1 : 0;
+    if (epi == 1 && E == 1 && eenv && atoi(eenv) == 2) epi = 2;   // split epilogue (pushers and inserters in different warps): experimental
     // Pruned search (knn_cluster.cuh): reference rows grouped by a coarse k-means, query rows grouped by nearest centroid,
     // whole clusters skipped by a rigorous lower bound.  B200MNN_PRUNE=0 never, =1 whenever the shape allows, unset: for
     // searches large enough to pay for the clustering.  B200MNN_CLUSTERS sets the number of clusters (power of two).
@@ -2624,7 +2644,8 @@ int query_knn_device(const double* dX, int64_t n, const double* dQ, int64_t nq, 
 #define B200_LAUNCH_TS_E(NB)                       \
     do {                                           \
         if (epi == 2) B200_LAUNCH_TS(1, NB, 2);    \
-        else if (epi == 1) B200_LAUNCH_TS(1, NB, 1);    \
+        else if (epi == 1 && E == 1) B200_LAUNCH_TS(1, NB, 1);    \
+        else if (epi == 1) B200_LAUNCH_TS(2, NB, 1);    \
         else if (E == 1) B200_LAUNCH_TS(1, NB, 0); \
         else B200_LAUNCH_TS(2, NB, 0);             \
     } while (0)

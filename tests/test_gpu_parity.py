@@ -297,10 +297,12 @@ def test_find_mutual_nn_pipelined_upload(monkeypatch, col_major, prune):
 
 
 @pytest.mark.parametrize("epi", ["0", "1"])
-@pytest.mark.parametrize("n,nq,d,k", [(70000, 20000, 50, 20), (5000, 3000, 17, 24), (3000, 1000, 120, 5)])
+@pytest.mark.parametrize("n,nq,d,k", [(70000, 20000, 50, 20), (5000, 3000, 17, 24), (3000, 1000, 120, 5), (70000, 20000, 50, 30),
+                                      (4000, 2500, 33, 26)])
 def test_query_knn_both_epilogues(monkeypatch, epi, n, nq, d, k):
     """The TS kernel's two epilogues (B200MNN_EPI=1: per-thread register lists, the default; 0: replace-the-maximum lists)
-    give the same exact answer, with the cluster plan on (first shape) and off."""
+    give the same exact answer, with the cluster plan on (70000-row shapes) and off; k = 26 / 30 use lists of 64 candidates per
+    row (32 per thread in the register-list epilogue)."""
     monkeypatch.setenv("B200MNN_EPI", epi)
     X, Q = synth.pc_batches(2, [n, nq], d=d, ncomp=6)
     res = bb.queryKNN(X, Q, k)
