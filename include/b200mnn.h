@@ -71,7 +71,9 @@ int b200mnn_query_knn(const double* X, int64_t n, const double* Q, int64_t nq, i
 
 /* findMutualNN(data1, data2, k1, k2): W21 = kNN of data1 rows in data2 (k2 each), W12 = kNN of data2 rows in data1
  * (k1 each), then the mutual pairs in the order of src/find_mutual_nns.cpp:23-37.
- * first_out/second_out: capacity entries each (n1*min(k2,n2) always suffices); *np_out = number of pairs. 1-based. */
+ * first_out/second_out: capacity entries each (n1*min(k2,n2) always suffices); *np_out = number of pairs. 1-based.
+ * From 262 144 rows per batch the uploads are pipelined: data1 crosses PCIe first, data2 follows in row chunks that are
+ * searched against data1 as they land (same result; INTEGRATION.md section 6 lists the switches). */
 int b200mnn_find_mutual_nn(const double* data1, int64_t n1, const double* data2, int64_t n2, int d, int k1, int k2,
                            int col_major, int32_t* first_out, int32_t* second_out, int64_t capacity, int64_t* np_out);
 
