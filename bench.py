@@ -525,7 +525,7 @@ def run_b200(args):
                          "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
                          "traffic_note": f"DRAM bytes (read + write) of one first-tier launch at 1M x 1M from the committed ncu --set full capture ({traffic_file}); "
                                          "a profiler figure, so stamped from the file, not measured in this run; captured from the working tree "
-                                         "committed as 916a58c (the kernel has not changed since)",
+                                         "committed as 916a58c (the epilogue of this kernel instance has not changed since; later commits only added the 64-candidate variant)",
                          "kernel": "knn_candidates_ts_kernel<1,1,1> (tcgen05 TS mode: query operand in TMEM, one-term fp16 tier, per-thread register-list epilogue; its three-term launches on the uncertified queries are included)",
                          "kernel_ms_per_launch": kernel_ms_max / max(kernel_launches / world, 1),
                          "kernel_share_of_step": kernel_ms_max / total_ms,
